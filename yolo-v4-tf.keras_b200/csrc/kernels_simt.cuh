@@ -1,0 +1,249 @@
+// CUDA-core kernels: fp32 implicit-GEMM conv (parity mode / debug reference for the tcgen05 path),
+// SPP max-pool, synthetic input fill, L2 flush.
+//
+// Activation layout ("padded-flat"): every activation tensor is stored NHWC with a 1-pixel zero halo,
+// rows = N*(H+2)*(W+2), row r = (n*(H+2) + h+1)*(W+2) + (w+1), `ld` channels per row (a tensor may be a
+// channel slice [ch_off, ch_off+C) of a wider concat buffer).  The halo is zeroed once at allocation and
+// never written, so a 3x3 'same' conv is a plain GEMM whose A rows are the output row shifted by
+// (kh-1)*(W+2) + (kw-1), and ZeroPadding2D(((1,0),(1,0))) of the stride-2 convs (custom_layers.py:10)
+// is the halo itself.
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace y4 {
+
+enum { ACT_LINEAR = 0, ACT_LEAKY = 1, ACT_MISH = 2 };
+
+struct SimtConvParams {
+    const void* in;            // padded-flat activations (TIn) or raw image (float, RAW=true)
+    int in_ld, in_choff;       // channels per row of the underlying buffer, first channel of the view
+    int in_Hp, in_Wp;          // padded dims of the input (RAW: unpadded H, W)
+    const float* w;            // [K][cout_pad] fp32, K index = (kh*k + kw)*cin + c   (HWIO, utils.py:42)
+    const float* bias;         // [cout_pad] folded BN bias / head bias
+    int K, cin, ksize, stride, cout, cout_pad;
+    void* out;                 // TOut (or float when out_f32)
+    int out_ld, out_choff;
+    int N, OH, OW;             // logical output dims; M = N*(OH+2)*(OW+2) rows are swept, halo rows skipped
+    const void* res;           // optional residual (same dims as out), added AFTER the activation (custom_layers.py:44)
+    int res_ld, res_choff;
+    int act;
+    int upsample;              // 1: write each output pixel to the 2x2 block of a (2*OH, 2*OW) destination (UpSampling2D)
+    int out_f32;               // heads: destination is float regardless of TOut
+    long long M;
+};
+
+__device__ __forceinline__ float ld_as_float(const float* p) { return *p; }
+__device__ __forceinline__ float ld_as_float(const __half* p) { return __half2float(*p); }
+__device__ __forceinline__ void st_from_float(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st_from_float(__half* p, float v) { *p = __float2half_rn(v); }
+
+// Reference activation semantics (custom_layers.py:6-7,27-30), fp32, accurate libm functions.
+__device__ __forceinline__ float act_exact(float x, int act) {
+    if (act == ACT_MISH) {
+        float sp = (x > 20.f) ? x : log1pf(expf(x));
+        return x * tanhf(sp);
+    }
+    if (act == ACT_LEAKY) return x > 0.f ? x : 0.1f * x;
+    return x;
+}
+
+template <typename TIn, typename TOut, bool RAW>
+__global__ void __launch_bounds__(256) conv_simt_kernel(SimtConvParams p) {
+    __shared__ float As[16][64 + 4];
+    __shared__ float Bs[16][64];
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    const int OHp = p.OH + 2, OWp = p.OW + 2;
+
+    // A-load role: one output row per 4 threads
+    const int la_r = tid >> 2, la_k = (tid & 3) * 4;
+    const long long r = m0 + la_r;
+    int rn = 0, rhp = 0, rwp = 0;
+    bool interior = false;
+    if (r < p.M) {
+        rwp = (int)(r % OWp);
+        long long t = r / OWp;
+        rhp = (int)(t % OHp);
+        rn = (int)(t / OHp);
+        interior = (rhp >= 1 && rhp <= p.OH && rwp >= 1 && rwp <= p.OW);
+    }
+    const int pad = p.ksize / 2;
+    const TIn* in = reinterpret_cast<const TIn*>(p.in);
+
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+
+    for (int k0 = 0; k0 < p.K; k0 += 16) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int kk = k0 + la_k + j;
+            float v = 0.f;
+            if (interior && kk < p.K) {
+                int tap = kk / p.cin, c = kk - tap * p.cin;
+                int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+                if (RAW) {
+                    int ih = (rhp - 1) + kh - pad, iw = (rwp - 1) + kw - pad;   // 'same', stride 1, unpadded source
+                    if (ih >= 0 && ih < p.in_Hp && iw >= 0 && iw < p.in_Wp)
+                        v = ld_as_float(in + (((long long)rn * p.in_Hp + ih) * p.in_Wp + iw) * p.in_ld + p.in_choff + c);
+                } else {
+                    int ihp = (rhp - 1) * p.stride + kh - pad + 1;
+                    int iwp = (rwp - 1) * p.stride + kw - pad + 1;
+                    v = ld_as_float(in + (((long long)rn * p.in_Hp + ihp) * p.in_Wp + iwp) * p.in_ld + p.in_choff + c);
+                }
+            }
+            As[la_k + j][la_r] = v;
+        }
+        {
+            int kk = k0 + (tid >> 4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int col = n0 + (tid & 15) * 4 + j;
+                Bs[tid >> 4][(tid & 15) * 4 + j] = (kk < p.K && col < p.cout_pad) ? p.w[(long long)kk * p.cout_pad + col] : 0.f;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; kk++) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; j++) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+
+    // epilogue: bias -> activation -> (+ residual) -> store
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        long long rr = m0 + ty * 4 + i;
+        if (rr >= p.M) continue;
+        int wp = (int)(rr % OWp);
+        long long t = rr / OWp;
+        int hp = (int)(t % OHp);
+        int n = (int)(t / OHp);
+        if (!(hp >= 1 && hp <= p.OH && wp >= 1 && wp <= p.OW)) continue;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int col = n0 + tx * 4 + j;
+            if (col >= p.cout) continue;
+            float v = act_exact(acc[i][j] + p.bias[col], p.act);
+            if (p.res) v += ld_as_float(reinterpret_cast<const TOut*>(p.res) + rr * p.res_ld + p.res_choff + col);
+            if (p.upsample) {
+                int DHp = 2 * p.OH + 2, DWp = 2 * p.OW + 2;
+#pragma unroll
+                for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+                    for (int dx = 0; dx < 2; dx++) {
+                        long long dr = ((long long)n * DHp + 2 * (hp - 1) + 1 + dy) * DWp + 2 * (wp - 1) + 1 + dx;
+                        st_from_float(reinterpret_cast<TOut*>(p.out) + dr * p.out_ld + p.out_choff + col, v);
+                    }
+            } else if (p.out_f32) {
+                reinterpret_cast<float*>(p.out)[rr * p.out_ld + p.out_choff + col] = v;
+            } else {
+                st_from_float(reinterpret_cast<TOut*>(p.out) + rr * p.out_ld + p.out_choff + col, v);
+            }
+        }
+    }
+}
+
+// SPP (custom_layers.py:130-134): mp13 | mp9 | mp5 | x, stride 1, 'same' (out-of-range cells ignored).
+// One thread per (n,h,w,c): nested windows 5 c 9 c 13 share one sweep.
+struct SppParams {
+    void* buf;            // concat buffer (N, H+2, W+2, ld)
+    int ld, N, H, W, C;   // C = channels of x; x lives at channel offset 3*C, outputs at 0, C, 2*C
+};
+
+template <typename T>
+__global__ void spp_kernel(SppParams p) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)p.N * p.H * p.W * p.C;
+    if (i >= total) return;
+    int c = (int)(i % p.C);
+    long long t = i / p.C;
+    int w = (int)(t % p.W); t /= p.W;
+    int h = (int)(t % p.H);
+    int n = (int)(t / p.H);
+    const int Hp = p.H + 2, Wp = p.W + 2;
+    T* base = reinterpret_cast<T*>(p.buf);
+    float m5 = -INFINITY, m9 = -INFINITY, m13 = -INFINITY;
+    for (int dy = -6; dy <= 6; dy++) {
+        int hh = h + dy;
+        if (hh < 0 || hh >= p.H) continue;
+        for (int dx = -6; dx <= 6; dx++) {
+            int ww = w + dx;
+            if (ww < 0 || ww >= p.W) continue;
+            float v = ld_as_float(base + (((long long)n * Hp + hh + 1) * Wp + ww + 1) * p.ld + 3 * p.C + c);
+            int ady = dy < 0 ? -dy : dy, adx = dx < 0 ? -dx : dx;
+            int d = ady > adx ? ady : adx;
+            m13 = fmaxf(m13, v);
+            if (d <= 4) m9 = fmaxf(m9, v);
+            if (d <= 2) m5 = fmaxf(m5, v);
+        }
+    }
+    long long o = (((long long)n * Hp + h + 1) * Wp + w + 1) * p.ld + c;
+    st_from_float(base + o, m13);
+    st_from_float(base + o + p.C, m9);
+    st_from_float(base + o + 2 * p.C, m5);
+}
+
+// splitmix64-style hash -> [0,1) with 24 random bits; bit-identical to oracle/y4_oracle.py:hash_uniform.
+__device__ __forceinline__ float hash_uniform(uint64_t idx, uint64_t seed) {
+    uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull;
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
+__global__ void synth_fill_kernel(float* img, uint64_t seed, uint64_t first_elem, long long count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < count; i += stride) img[i] = hash_uniform(first_elem + (uint64_t)i, seed);
+}
+
+__global__ void l2_flush_kernel(float4* buf, long long n, float v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) buf[i] = make_float4(v, v, v, v);
+}
+
+// packed user heads (B,g,g,C) -> padded-flat fp32 head buffer (ld = ld_out)
+__global__ void scatter_head_kernel(const float* src, float* dst, int N, int g, int C, int ld_out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * g * g * C;
+    if (i >= total) return;
+    int c = (int)(i % C);
+    long long t = i / C;
+    int w = (int)(t % g); t /= g;
+    int h = (int)(t % g);
+    int n = (int)(t / g);
+    dst[(((long long)n * (g + 2) + h + 1) * (g + 2) + w + 1) * ld_out + c] = src[i];
+}
+
+// padded-flat (any T) view -> packed NHWC float (debug / y4_forward_heads)
+template <typename T>
+__global__ void gather_view_kernel(const T* src, float* dst, int N, int H, int W, int C, int ld, int choff) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * H * W * C;
+    if (i >= total) return;
+    int c = (int)(i % C);
+    long long t = i / C;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    dst[i] = ld_as_float(src + (((long long)n * (H + 2) + h + 1) * (W + 2) + w + 1) * ld + choff + c);
+}
+
+}  // namespace y4

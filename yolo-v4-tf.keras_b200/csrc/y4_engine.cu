@@ -1,0 +1,842 @@
+// liby4.so — engine host side: graph planning, darknet loader, launch schedule, C-ABI (include/y4.h).
+//
+// Graph planning follows the reference builder order (custom_layers.py:100-198) so conv index ==
+// Keras creation order == darknet file order (utils.py:12-53).  Planning decisions (all static):
+//   * every Concatenate is eliminated: producers write straight into channel slices of the concat buffer;
+//   * every residual Add is fused into the epilogue of the producing 3x3 conv (add AFTER activation);
+//   * both UpSampling2D are fused into the producing 1x1 conv's store (2x2 replicated write);
+//   * BatchNorm (eps 1e-3) is folded into weights/bias at load time;
+//   * SPP is one kernel writing the three pooled slices next to its input inside the concat buffer.
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cuda.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/y4.h"
+#include "kernels_simt.cuh"
+#include "decode_nms.cuh"
+#include "conv_tc.cuh"
+
+using namespace y4;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Buf {
+    void* ptr = nullptr;
+    int H = 0, W = 0, C = 0;   // logical spatial dims, total channels (ld)
+    int elt = 0;               // bytes per element
+    size_t bytes = 0;
+};
+struct View {
+    int buf = -1, choff = 0, C = 0, H = 0, W = 0;
+};
+struct SymOp {
+    int kind = 0;              // 0 conv, 1 add, 2 concat, 3 maxpool, 4 upsample
+    std::string out;
+    std::vector<std::string> ins;
+    int idx = -1, cin = 0, cout = 0, k = 0, stride = 1, bn = 1, act = 0, pool = 0;
+    int channels = 0, scale = 1;
+};
+
+struct ConvOp {
+    int idx = 0, cin = 0, cout = 0, cout_pad = 0, k = 1, stride = 1, bn = 1, act = 0;
+    int K = 0;
+    int raw_in = 0;
+    View in, out, res;
+    int has_res = 0, upsample = 0, out_f32 = 0;
+    int N_OH = 0;              // output spatial size
+    float* d_w32 = nullptr;    // [K][cout_pad]
+    float* d_bias = nullptr;   // [cout_pad]
+    __half* d_w16 = nullptr;   // [cout_pad][K]  (tcgen05 path)
+    int kind = 0;              // 0 simt, 1 tc flat, 2 tc box
+    TcConvPlan tc;             // tensor maps + tile config (conv_tc.cuh)
+    std::string out_name;
+};
+struct Step { int type; int conv; };   // type 0 conv, 1 spp
+
+}  // namespace
+
+struct y4_engine {
+    y4_config cfg{};
+    std::string err;
+    cudaStream_t stream = nullptr;
+    int elt = 2;                       // activation element size
+    std::vector<Buf> bufs;
+    std::map<std::string, View> views;
+    std::vector<ConvOp> convs;
+    std::vector<Step> steps;
+    View spp_view;                     // concat buffer view of the SPP
+    int spp_C = 0;
+    float* d_img = nullptr;
+    int g[3] = {0, 0, 0};
+    int N = 0;                         // boxes per image
+    int head_ld = 0;
+    int head_buf[3] = {-1, -1, -1};
+    float* d_user_heads[3] = {nullptr, nullptr, nullptr};
+    unsigned long long* d_cand_keys = nullptr;
+    int* d_cand_count = nullptr;
+    float4* d_boxes = nullptr;
+    float* d_out_boxes = nullptr; float* d_out_scores = nullptr; float* d_out_classes = nullptr;
+    int* d_out_valid = nullptr; int* d_out_idx = nullptr; int* d_overflow = nullptr;
+    bool weights_loaded = false;
+    int64_t launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float4* d_flush = nullptr; size_t flush_elems = 0;
+    ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
+    void* d_gather = nullptr; size_t gather_bytes = 0;
+};
+
+namespace {
+
+int fail(y4_engine* e, int code, const std::string& msg) {
+    if (e) e->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CUDA_TRY(e, call)                                                                         \
+    do {                                                                                          \
+        cudaError_t err__ = (call);                                                               \
+        if (err__ != cudaSuccess)                                                                 \
+            return fail((e), Y4_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(err__)); \
+    } while (0)
+
+// ---- symbolic builder (mirror of custom_layers.py:5-198; kept as data, cf. oracle/netspec.py) -------
+struct Builder {
+    std::vector<SymOp> ops;
+    std::map<std::string, std::pair<int, int>> meta;   // name -> (channels, scale)
+    int nconv = 0, nadd = 0, ncat = 0;
+    Builder() { meta["img"] = {3, 1}; }
+    std::string conv(const std::string& x, int filters, int k, bool down = false, int act = ACT_LEAKY, bool bn = true) {
+        SymOp o; o.kind = 0; o.out = "c" + std::to_string(nconv); o.ins = {x};
+        o.idx = nconv++; o.cin = meta[x].first; o.cout = filters; o.k = k; o.stride = down ? 2 : 1;
+        o.bn = bn; o.act = act; o.channels = filters; o.scale = meta[x].second * (down ? 2 : 1);
+        meta[o.out] = {o.channels, o.scale}; ops.push_back(o); return o.out;
+    }
+    std::string add(const std::string& a, const std::string& b) {
+        SymOp o; o.kind = 1; o.out = "r" + std::to_string(++nadd); o.ins = {a, b};
+        o.channels = meta[a].first; o.scale = meta[a].second;
+        meta[o.out] = {o.channels, o.scale}; ops.push_back(o); return o.out;
+    }
+    std::string concat(const std::vector<std::string>& parts) {
+        SymOp o; o.kind = 2; o.out = "cat" + std::to_string(++ncat); o.ins = parts;
+        o.scale = meta[parts[0]].second; o.channels = 0;
+        for (auto& p : parts) o.channels += meta[p].first;
+        meta[o.out] = {o.channels, o.scale}; ops.push_back(o); return o.out;
+    }
+    std::string maxpool(const std::string& x, int size) {
+        SymOp o; o.kind = 3; o.out = "mp" + std::to_string(size); o.ins = {x}; o.pool = size;
+        o.channels = meta[x].first; o.scale = meta[x].second;
+        meta[o.out] = {o.channels, o.scale}; ops.push_back(o); return o.out;
+    }
+    std::string upsample(const std::string& x) {
+        SymOp o; o.kind = 4; o.out = "up_" + x; o.ins = {x};
+        o.channels = meta[x].first; o.scale = meta[x].second / 2;
+        meta[o.out] = {o.channels, o.scale}; ops.push_back(o); return o.out;
+    }
+    std::string residual(const std::string& x, int f1, int f2, int act) {          // custom_layers.py:34-44
+        std::string y = conv(x, f1, 1, false, act);
+        y = conv(y, f2, 3, false, act);
+        return add(x, y);
+    }
+    std::string csp(std::string x, int out, int repeat, bool bottleneck = false) {  // custom_layers.py:47-69
+        std::string route = conv(x, out, 1, false, ACT_MISH);
+        x = conv(x, out, 1, false, ACT_MISH);
+        for (int i = 0; i < repeat; i++) x = residual(x, bottleneck ? out / 2 : out, out, ACT_MISH);
+        x = conv(x, out, 1, false, ACT_MISH);
+        return concat({x, route});
+    }
+    void build(int num_classes, std::string heads[3]) {
+        std::string x = conv("img", 32, 3);                       // custom_layers.py:101 (leaky by default arg)
+        x = conv(x, 64, 3, true);
+        x = csp(x, 64, 1, true);
+        x = conv(x, 64, 1, false, ACT_MISH);
+        x = conv(x, 128, 3, true, ACT_MISH);
+        x = csp(x, 64, 2);
+        x = conv(x, 128, 1, false, ACT_MISH);
+        x = conv(x, 256, 3, true, ACT_MISH);
+        x = csp(x, 128, 8);
+        x = conv(x, 256, 1, false, ACT_MISH);
+        std::string route0 = x;
+        x = conv(x, 512, 3, true, ACT_MISH);
+        x = csp(x, 256, 8);
+        x = conv(x, 512, 1, false, ACT_MISH);
+        std::string route1 = x;
+        x = conv(x, 1024, 3, true, ACT_MISH);
+        x = csp(x, 512, 4);
+        x = conv(x, 1024, 1, false, ACT_MISH);
+        x = conv(x, 512, 1); x = conv(x, 1024, 3); x = conv(x, 512, 1);
+        std::string m13 = maxpool(x, 13), m9 = maxpool(x, 9), m5 = maxpool(x, 5);
+        x = concat({m13, m9, m5, x});                             // custom_layers.py:130-134
+        x = conv(x, 512, 1); x = conv(x, 1024, 3);
+        std::string route2 = conv(x, 512, 1);
+        const int nout = 3 * (num_classes + 5);
+        // neck, custom_layers.py:141-198
+        x = conv(route2, 256, 1);
+        std::string up = upsample(x);
+        std::string r1 = conv(route1, 256, 1);
+        x = concat({r1, up});
+        const int seq1[5][2] = {{256, 1}, {512, 3}, {256, 1}, {512, 3}, {256, 1}};
+        for (auto& s : seq1) x = conv(x, s[0], s[1]);
+        std::string route1b = x;
+        x = conv(x, 128, 1);
+        up = upsample(x);
+        std::string r0 = conv(route0, 128, 1);
+        x = concat({r0, up});
+        const int seq0[5][2] = {{128, 1}, {256, 3}, {128, 1}, {256, 3}, {128, 1}};
+        for (auto& s : seq0) x = conv(x, s[0], s[1]);
+        std::string route0b = x;
+        x = conv(x, 256, 3);
+        heads[0] = conv(x, nout, 1, false, ACT_LINEAR, false);
+        x = conv(route0b, 256, 3, true);
+        x = concat({x, route1b});
+        for (auto& s : seq1) x = conv(x, s[0], s[1]);
+        std::string route1c = x;
+        x = conv(x, 512, 3);
+        heads[1] = conv(x, nout, 1, false, ACT_LINEAR, false);
+        x = conv(route1c, 512, 3, true);
+        x = concat({x, route2});
+        const int seq2[5][2] = {{512, 1}, {1024, 3}, {512, 1}, {1024, 3}, {512, 1}};
+        for (auto& s : seq2) x = conv(x, s[0], s[1]);
+        x = conv(x, 1024, 3);
+        heads[2] = conv(x, nout, 1, false, ACT_LINEAR, false);
+    }
+};
+
+int alloc_buf(y4_engine* e, int H, int W, int C, int elt) {
+    Buf b; b.H = H; b.W = W; b.C = C; b.elt = elt;
+    b.bytes = (size_t)e->cfg.max_batch * (H + 2) * (W + 2) * C * elt;
+    if (cudaMalloc(&b.ptr, b.bytes) != cudaSuccess) return -1;
+    if (cudaMemset(b.ptr, 0, b.bytes) != cudaSuccess) return -1;     // halo stays zero forever
+    e->bufs.push_back(b);
+    return (int)e->bufs.size() - 1;
+}
+
+int plan_graph(y4_engine* e) {
+    const int S = e->cfg.img_size, nc = e->cfg.num_classes;
+    Builder b; std::string heads[3];
+    b.build(nc, heads);
+    std::map<std::string, View> placed;         // tensors that live inside a concat buffer
+    std::map<std::string, std::string> fused_add, res_of, up_src;
+    for (auto& o : b.ops) {
+        if (o.kind == 2) {
+            int hw = S / o.scale;
+            int bi = alloc_buf(e, hw, hw, o.channels, e->elt);
+            if (bi < 0) return fail(e, Y4_ERR_CUDA, "cudaMalloc failed for concat buffer " + o.out);
+            View v; v.buf = bi; v.choff = 0; v.C = o.channels; v.H = v.W = hw;
+            e->views[o.out] = v;
+            int off = 0;
+            for (auto& part : o.ins) {
+                View pv = v; pv.choff = off; pv.C = b.meta[part].first;
+                placed[part] = pv; off += pv.C;
+            }
+        }
+    }
+    for (auto& o : b.ops) {
+        if (o.kind == 1) { fused_add[o.ins[1]] = o.out; res_of[o.ins[1]] = o.ins[0]; }
+        if (o.kind == 4) { up_src[o.ins[0]] = o.out; }
+    }
+    View img; img.buf = -1; img.C = 3; img.H = img.W = S;
+    e->views["img"] = img;
+    bool spp_done = false;
+    for (auto& o : b.ops) {
+        if (o.kind == 0) {
+            ConvOp c;
+            c.idx = o.idx; c.cin = o.cin; c.cout = o.cout; c.k = o.k; c.stride = o.stride; c.bn = o.bn; c.act = o.act;
+            c.K = o.k * o.k * o.cin; c.cout_pad = (o.cout + 63) / 64 * 64;
+            c.raw_in = (o.ins[0] == "img");
+            if (!e->views.count(o.ins[0])) return fail(e, Y4_ERR_ARG, "planner: input not materialised: " + o.ins[0]);
+            c.in = e->views[o.ins[0]];
+            const int hw = S / o.scale;
+            c.N_OH = hw;
+            c.out_name = o.out;
+            if (fused_add.count(o.out)) {
+                int bi = alloc_buf(e, hw, hw, o.cout, e->elt);
+                if (bi < 0) return fail(e, Y4_ERR_CUDA, "cudaMalloc failed");
+                View v; v.buf = bi; v.C = o.cout; v.H = v.W = hw;
+                c.out = v; c.has_res = 1; c.res = e->views[res_of[o.out]];
+                c.out_name = fused_add[o.out];
+                e->views[c.out_name] = v;
+            } else if (up_src.count(o.out)) {
+                const std::string& upn = up_src[o.out];
+                if (!placed.count(upn)) return fail(e, Y4_ERR_ARG, "planner: upsample not feeding a concat");
+                c.out = placed[upn]; c.upsample = 1; c.out_name = upn;
+                e->views[upn] = c.out;
+            } else if (placed.count(o.out)) {
+                c.out = placed[o.out];
+                e->views[o.out] = c.out;
+            } else {
+                const bool head = !o.bn;
+                int bi = alloc_buf(e, hw, hw, head ? c.cout_pad : o.cout, head ? 4 : e->elt);
+                if (bi < 0) return fail(e, Y4_ERR_CUDA, "cudaMalloc failed");
+                View v; v.buf = bi; v.C = o.cout; v.H = v.W = hw;
+                c.out = v; c.out_f32 = head;
+                e->views[o.out] = v;
+            }
+            e->convs.push_back(c);
+            e->steps.push_back({0, (int)e->convs.size() - 1});
+        } else if (o.kind == 3) {
+            if (!spp_done) {
+                spp_done = true;
+                View x = e->views[o.ins[0]];
+                if (!placed.count("mp13") || placed["mp13"].choff != 0 || placed["mp9"].choff != x.C ||
+                    placed["mp5"].choff != 2 * x.C || x.choff != 3 * x.C || placed["mp13"].buf != x.buf)
+                    return fail(e, Y4_ERR_ARG, "planner: unexpected SPP layout");
+                e->spp_view = x; e->spp_C = x.C;
+                e->steps.push_back({1, -1});
+            }
+            e->views[o.out] = placed[o.out];
+        }
+    }
+    for (int i = 0; i < 3; i++) {
+        e->head_buf[i] = e->views[heads[i]].buf;
+        e->g[i] = S / e->cfg.strides[i];
+        if (e->views[heads[i]].H != e->g[i]) return fail(e, Y4_ERR_ARG, "strides do not match the network's head scales (8,16,32)");
+    }
+    e->head_ld = e->bufs[e->head_buf[0]].C;
+    e->N = 3 * (e->g[0] * e->g[0] + e->g[1] * e->g[1] + e->g[2] * e->g[2]);
+    return Y4_OK;
+}
+
+template <typename TIn, typename TOut>
+void launch_simt_t(y4_engine* e, const ConvOp& c, const SimtConvParams& p) {
+    dim3 grid((unsigned)((p.M + 63) / 64), (unsigned)((c.cout + 63) / 64));
+    if (c.raw_in) conv_simt_kernel<float, TOut, true><<<grid, 256, 0, e->stream>>>(p);
+    else conv_simt_kernel<TIn, TOut, false><<<grid, 256, 0, e->stream>>>(p);
+}
+
+void launch_simt(y4_engine* e, const ConvOp& c, int batch) {
+    SimtConvParams p{};
+    if (c.raw_in) {
+        p.in = e->d_img; p.in_ld = 3; p.in_choff = 0; p.in_Hp = e->cfg.img_size; p.in_Wp = e->cfg.img_size;
+    } else {
+        const Buf& ib = e->bufs[c.in.buf];
+        p.in = ib.ptr; p.in_ld = ib.C; p.in_choff = c.in.choff; p.in_Hp = ib.H + 2; p.in_Wp = ib.W + 2;
+    }
+    p.w = c.d_w32; p.bias = c.d_bias; p.K = c.K; p.cin = c.cin; p.ksize = c.k; p.stride = c.stride;
+    p.cout = c.cout; p.cout_pad = c.cout_pad;
+    const Buf& ob = e->bufs[c.out.buf];
+    p.out = ob.ptr; p.out_ld = ob.C; p.out_choff = c.out.choff;
+    p.N = batch; p.OH = c.N_OH; p.OW = c.N_OH;
+    if (c.has_res) { const Buf& rb = e->bufs[c.res.buf]; p.res = rb.ptr; p.res_ld = rb.C; p.res_choff = c.res.choff; }
+    p.act = c.act; p.upsample = c.upsample; p.out_f32 = c.out_f32;
+    p.M = (long long)batch * (c.N_OH + 2) * (c.N_OH + 2);
+    if (e->elt == 4) launch_simt_t<float, float>(e, c, p);
+    else launch_simt_t<__half, __half>(e, c, p);
+    e->launches++;
+}
+
+void launch_spp(y4_engine* e, int batch) {
+    const Buf& b = e->bufs[e->spp_view.buf];
+    SppParams p{b.ptr, b.C, batch, b.H, b.W, e->spp_C};
+    long long total = (long long)batch * b.H * b.W * e->spp_C;
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (e->elt == 4) spp_kernel<float><<<blocks, 256, 0, e->stream>>>(p);
+    else spp_kernel<__half><<<blocks, 256, 0, e->stream>>>(p);
+    e->launches++;
+}
+
+int run_conv(y4_engine* e, const ConvOp& c, int batch) {
+    if (c.kind == 0) { launch_simt(e, c, batch); return Y4_OK; }
+    int rc = tc_launch(c.tc, batch, e->stream);
+    if (rc != 0) return fail(e, Y4_ERR_CUDA, "tcgen05 conv launch failed for conv " + std::to_string(c.idx));
+    e->launches++;
+    return Y4_OK;
+}
+
+int run_forward(y4_engine* e, int batch) {
+    for (auto& s : e->steps) {
+        if (s.type == 0) { int rc = run_conv(e, e->convs[s.conv], batch); if (rc) return rc; }
+        else launch_spp(e, batch);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    return Y4_OK;
+}
+
+int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, const float* const* user_heads) {
+    DecodeParams d{};
+    const int nc = e->cfg.num_classes;
+    int cells = 0, boxes = 0;
+    for (int i = 0; i < 3; i++) {
+        if (user_heads) { d.head[i] = user_heads[i]; d.ld[i] = 3 * (5 + nc); d.padded[i] = 0; }
+        else { d.head[i] = (const float*)e->bufs[e->head_buf[i]].ptr; d.ld[i] = e->head_ld; d.padded[i] = 1; }
+        d.g[i] = e->g[i]; d.stride[i] = (float)e->cfg.strides[i];
+        d.xyscale[i] = (float)e->cfg.xyscale[i];
+        d.xyoff[i] = (float)(0.5 * (e->cfg.xyscale[i] - 1.0));
+        d.cell_off[i] = cells; d.box_off[i] = boxes;
+        cells += e->g[i] * e->g[i]; boxes += 3 * e->g[i] * e->g[i];
+    }
+    d.cell_off[3] = cells;
+    for (int i = 0; i < 18; i++) d.anchors[i] = e->cfg.anchors[i];
+    d.nc = nc; d.C = 5 + nc; d.N = e->N; d.batch = batch; d.img_size = (float)e->cfg.img_size; d.score_thr = score_thr;
+    d.cand_keys = e->d_cand_keys; d.cand_count = e->d_cand_count; d.boxes = e->d_boxes;
+    CUDA_TRY(e, cudaMemsetAsync(e->d_cand_count, 0, sizeof(int) * batch, e->stream));
+    long long warps = (long long)batch * cells;
+    unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    decode_filter_kernel<<<blocks, 256, 0, e->stream>>>(d);
+    NmsParams n{};
+    n.cand_keys = e->d_cand_keys; n.cand_count = e->d_cand_count; n.boxes = e->d_boxes;
+    n.N = e->N; n.nc = nc; n.max_boxes = e->cfg.max_boxes; n.iou_thr = iou_thr;
+    n.out_boxes = e->d_out_boxes; n.out_scores = e->d_out_scores; n.out_classes = e->d_out_classes;
+    n.out_valid = e->d_out_valid; n.out_idx = e->d_out_idx; n.overflow = e->d_overflow;
+    nms_kernel<<<batch, kNmsThreads, kNmsSmemBytes, e->stream>>>(n);
+    e->launches += 2;
+    CUDA_TRY(e, cudaGetLastError());
+    return Y4_OK;
+}
+
+int fetch(y4_engine* e, int batch, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx) {
+    const int mb = e->cfg.max_boxes;
+    int overflow = 0;
+    if (boxes) CUDA_TRY(e, cudaMemcpyAsync(boxes, e->d_out_boxes, sizeof(float) * 4 * mb * batch, cudaMemcpyDeviceToHost, e->stream));
+    if (scores) CUDA_TRY(e, cudaMemcpyAsync(scores, e->d_out_scores, sizeof(float) * mb * batch, cudaMemcpyDeviceToHost, e->stream));
+    if (classes) CUDA_TRY(e, cudaMemcpyAsync(classes, e->d_out_classes, sizeof(float) * mb * batch, cudaMemcpyDeviceToHost, e->stream));
+    if (valid) CUDA_TRY(e, cudaMemcpyAsync(valid, e->d_out_valid, sizeof(int) * batch, cudaMemcpyDeviceToHost, e->stream));
+    if (cand_idx) CUDA_TRY(e, cudaMemcpyAsync(cand_idx, e->d_out_idx, sizeof(int) * mb * batch, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(&overflow, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (overflow) {
+        cudaMemsetAsync(e->d_overflow, 0, sizeof(int), e->stream);
+        return fail(e, Y4_ERR_CAPACITY, "more than Y4_MAX_CANDIDATES (8192) candidates above score_threshold in one image");
+    }
+    return Y4_OK;
+}
+
+int check_batch(y4_engine* e, int batch) {
+    if (!e) return Y4_ERR_ARG;
+    if (batch < 1 || batch > e->cfg.max_batch) return fail(e, Y4_ERR_ARG, "batch must be in [1, max_batch]");
+    return Y4_OK;
+}
+
+int upload_weights(y4_engine* e, const unsigned char* data, size_t nbytes) {
+    // utils.py:12-53: 5 x int32 header, then per conv [beta,gamma,mean,var | bias] + OIHW weights
+    size_t need = 20;
+    for (auto& c : e->convs) need += 4ull * ((c.bn ? 4 * c.cout : c.cout) + (size_t)c.cout * c.cin * c.k * c.k);
+    if (nbytes != need)
+        return fail(e, Y4_ERR_WEIGHTS, "darknet weights: expected " + std::to_string(need) + " bytes, got " + std::to_string(nbytes));
+    size_t off = 20;
+    std::vector<float> w32, bias;
+    std::vector<__half> w16;
+    for (auto& c : e->convs) {
+        const float* f = reinterpret_cast<const float*>(data + off);
+        std::vector<double> scale(c.cout, 1.0);
+        bias.assign(c.cout_pad, 0.f);
+        if (c.bn) {
+            const float *beta = f, *gamma = f + c.cout, *mean = f + 2 * c.cout, *var = f + 3 * c.cout;
+            for (int o = 0; o < c.cout; o++) {
+                scale[o] = (double)gamma[o] / std::sqrt((double)var[o] + 1e-3);        // Keras BN eps (custom_layers.py:26)
+                bias[o] = (float)((double)beta[o] - (double)mean[o] * scale[o]);
+            }
+            f += 4 * c.cout; off += 16ull * c.cout;
+        } else {
+            for (int o = 0; o < c.cout; o++) bias[o] = f[o];
+            f += c.cout; off += 4ull * c.cout;
+        }
+        // file: [cout][cin][kh][kw]  ->  K index (kh*k+kw)*cin + c   (HWIO flattened, utils.py:42)
+        w32.assign((size_t)c.K * c.cout_pad, 0.f);
+        w16.assign((size_t)c.cout_pad * c.K, __float2half(0.f));
+        const int kk = c.k * c.k;
+        for (int o = 0; o < c.cout; o++)
+            for (int ci = 0; ci < c.cin; ci++)
+                for (int t = 0; t < kk; t++) {
+                    float v = (float)((double)f[((size_t)o * c.cin + ci) * kk + t] * scale[o]);
+                    size_t kidx = (size_t)t * c.cin + ci;
+                    w32[kidx * c.cout_pad + o] = v;
+                    w16[(size_t)o * c.K + kidx] = __float2half_rn(v);
+                }
+        off += 4ull * c.cout * c.cin * kk;
+        CUDA_TRY(e, cudaMemcpy(c.d_w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
+        CUDA_TRY(e, cudaMemcpy(c.d_w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+        CUDA_TRY(e, cudaMemcpy(c.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    }
+    e->weights_loaded = true;
+    return Y4_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int y4_default_config(y4_config* cfg) {
+    if (!cfg) return Y4_ERR_ARG;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->img_size = 416; cfg->num_classes = 80; cfg->max_batch = 1; cfg->precision = Y4_PREC_FP16; cfg->device = 0;
+    cfg->max_boxes = 100;
+    const int st[3] = {8, 16, 32};
+    const float an[18] = {12, 16, 19, 36, 40, 28, 36, 75, 76, 55, 72, 146, 142, 110, 192, 243, 459, 401};
+    const double xs[3] = {1.2, 1.1, 1.05};
+    for (int i = 0; i < 3; i++) { cfg->strides[i] = st[i]; cfg->xyscale[i] = xs[i]; }
+    for (int i = 0; i < 18; i++) cfg->anchors[i] = an[i];
+    cfg->iou_threshold = 0.413f; cfg->score_threshold = 0.3f;
+    return Y4_OK;
+}
+
+const char* y4_last_error(const y4_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int y4_create(y4_engine** out, const y4_config* cfg) {
+    if (!out || !cfg) return fail(nullptr, Y4_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (cfg->img_size < 32 || cfg->img_size % 32 != 0 || cfg->img_size > 2048)
+        return fail(nullptr, Y4_ERR_ARG, "img_size must be a multiple of the last stride (32)  [models.py:24]");
+    if (cfg->num_classes < 1 || cfg->num_classes > 255) return fail(nullptr, Y4_ERR_ARG, "num_classes must be in [1,255]");
+    if (cfg->max_boxes < 1 || cfg->max_boxes > kMaxBoxesCap || cfg->max_boxes * cfg->num_classes > kSelCap)
+        return fail(nullptr, Y4_ERR_ARG, "max_boxes must be in [1,128] and max_boxes*num_classes <= 8192");
+    if (cfg->max_batch < 1) return fail(nullptr, Y4_ERR_ARG, "max_batch must be >= 1");
+    if (cfg->precision < 0 || cfg->precision > 2) return fail(nullptr, Y4_ERR_ARG, "unknown precision");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, Y4_ERR_CUDA, "no CUDA device available (this engine has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, Y4_ERR_ARG, "bad device ordinal");
+    cudaDeviceProp prop;
+    if (cudaSetDevice(cfg->device) != cudaSuccess || cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess)
+        return fail(nullptr, Y4_ERR_CUDA, "cudaSetDevice failed");
+    if (prop.major != 10)
+        return fail(nullptr, Y4_ERR_CUDA, "device is not sm_100 (Blackwell B200); this library ships sm_100a code only");
+
+    y4_engine* e = new y4_engine();
+    e->cfg = *cfg;
+    e->elt = cfg->precision == Y4_PREC_FP32 ? 4 : 2;
+    auto bail = [&](int rc) { g_create_error = e->err; y4_destroy(e); return rc; };
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, "stream create failed"));
+    cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
+    int rc = plan_graph(e);
+    if (rc) return bail(rc);
+    const int S = cfg->img_size, B = cfg->max_batch, mb = cfg->max_boxes;
+#define CREATE_TRY(call) do { if ((call) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError()))); } while (0)
+    CREATE_TRY(cudaMalloc(&e->d_img, sizeof(float) * 3 * S * S * B));
+    for (auto& c : e->convs) {
+        CREATE_TRY(cudaMalloc(&c.d_w32, sizeof(float) * c.K * c.cout_pad));
+        CREATE_TRY(cudaMalloc(&c.d_w16, sizeof(__half) * c.K * c.cout_pad));
+        CREATE_TRY(cudaMalloc(&c.d_bias, sizeof(float) * c.cout_pad));
+    }
+    for (int i = 0; i < 3; i++)
+        CREATE_TRY(cudaMalloc(&e->d_user_heads[i], sizeof(float) * B * e->g[i] * e->g[i] * 3 * (5 + cfg->num_classes)));
+    CREATE_TRY(cudaMalloc(&e->d_cand_keys, sizeof(unsigned long long) * kCandCap * B));
+    CREATE_TRY(cudaMalloc(&e->d_cand_count, sizeof(int) * B));
+    CREATE_TRY(cudaMalloc(&e->d_boxes, sizeof(float4) * e->N * B));
+    CREATE_TRY(cudaMemset(e->d_boxes, 0, sizeof(float4) * e->N * B));
+    CREATE_TRY(cudaMalloc(&e->d_out_boxes, sizeof(float) * 4 * mb * B));
+    CREATE_TRY(cudaMalloc(&e->d_out_scores, sizeof(float) * mb * B));
+    CREATE_TRY(cudaMalloc(&e->d_out_classes, sizeof(float) * mb * B));
+    CREATE_TRY(cudaMalloc(&e->d_out_valid, sizeof(int) * B));
+    CREATE_TRY(cudaMalloc(&e->d_out_idx, sizeof(int) * mb * B));
+    CREATE_TRY(cudaMalloc(&e->d_overflow, sizeof(int)));
+    CREATE_TRY(cudaMemset(e->d_overflow, 0, sizeof(int)));
+    e->flush_elems = (size_t)(192u << 20) / sizeof(float4);      // 192 MB > 126 MB L2
+    CREATE_TRY(cudaMalloc(&e->d_flush, e->flush_elems * sizeof(float4)));
+    CREATE_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemBytes));
+    // tcgen05 plans (tensor maps need the buffer addresses, which are now fixed)
+    if (cfg->precision == Y4_PREC_FP16) {
+        for (auto& c : e->convs) {
+            TcConvDesc d{};
+            d.cin = c.cin; d.cout = c.cout; d.cout_pad = c.cout_pad; d.k = c.k; d.stride = c.stride; d.act = c.act;
+            d.raw_in = c.raw_in; d.max_batch = B; d.OH = c.N_OH;
+            if (!c.raw_in) { const Buf& ib = e->bufs[c.in.buf]; d.in = ib.ptr; d.in_ld = ib.C; d.in_choff = c.in.choff; d.in_H = ib.H; }
+            const Buf& ob = e->bufs[c.out.buf];
+            d.out = ob.ptr; d.out_ld = ob.C; d.out_choff = c.out.choff; d.out_f32 = c.out_f32; d.upsample = c.upsample;
+            if (c.has_res) { const Buf& rb = e->bufs[c.res.buf]; d.res = rb.ptr; d.res_ld = rb.C; d.res_choff = c.res.choff; }
+            d.w16 = c.d_w16; d.bias = c.d_bias;
+            std::string terr;
+            int kind = tc_plan(d, &c.tc, &terr);
+            if (kind < 0) return bail(fail(e, Y4_ERR_CUDA, "tcgen05 plan failed for conv " + std::to_string(c.idx) + ": " + terr));
+            c.kind = kind;
+        }
+    }
+    CREATE_TRY(cudaDeviceSynchronize());
+    *out = e;
+    return Y4_OK;
+}
+
+void y4_destroy(y4_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->comm) ncclCommDestroy(e->comm);
+    for (auto& b : e->bufs) cudaFree(b.ptr);
+    for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_bias); }
+    cudaFree(e->d_img);
+    for (int i = 0; i < 3; i++) cudaFree(e->d_user_heads[i]);
+    cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
+    cudaFree(e->d_out_boxes); cudaFree(e->d_out_scores); cudaFree(e->d_out_classes);
+    cudaFree(e->d_out_valid); cudaFree(e->d_out_idx); cudaFree(e->d_overflow);
+    cudaFree(e->d_flush); cudaFree(e->d_gather);
+    if (e->ev0) cudaEventDestroy(e->ev0);
+    if (e->ev1) cudaEventDestroy(e->ev1);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int y4_load_darknet_from_memory(y4_engine* e, const void* data, size_t nbytes) {
+    if (!e || !data) return e ? fail(e, Y4_ERR_ARG, "null data") : Y4_ERR_ARG;
+    cudaSetDevice(e->cfg.device);
+    return upload_weights(e, static_cast<const unsigned char*>(data), nbytes);
+}
+
+int y4_load_darknet(y4_engine* e, const char* path) {
+    if (!e || !path) return e ? fail(e, Y4_ERR_ARG, "null path") : Y4_ERR_ARG;
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(e, Y4_ERR_WEIGHTS, std::string("cannot open ") + path);
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<unsigned char> buf((size_t)sz);
+    size_t got = fread(buf.data(), 1, (size_t)sz, f);
+    fclose(f);
+    if (got != (size_t)sz) return fail(e, Y4_ERR_WEIGHTS, "short read");
+    return y4_load_darknet_from_memory(e, buf.data(), buf.size());
+}
+
+static int ready(y4_engine* e, int batch, bool need_weights) {
+    int rc = check_batch(e, batch);
+    if (rc) return rc;
+    if (need_weights && !e->weights_loaded) return fail(e, Y4_ERR_STATE, "weights not loaded (call y4_load_darknet first)");
+    cudaSetDevice(e->cfg.device);
+    return Y4_OK;
+}
+
+int y4_predict(y4_engine* e, const float* imgs, int32_t batch, float* boxes, float* scores, float* classes,
+               int32_t* valid, int32_t* cand_idx) {
+    int rc = ready(e, batch, true); if (rc) return rc;
+    if (!imgs) return fail(e, Y4_ERR_ARG, "null imgs");
+    const size_t n = (size_t)batch * e->cfg.img_size * e->cfg.img_size * 3;
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_img, imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    rc = run_forward(e, batch); if (rc) return rc;
+    rc = run_decode_nms(e, batch, e->cfg.iou_threshold, e->cfg.score_threshold, nullptr); if (rc) return rc;
+    return fetch(e, batch, boxes, scores, classes, valid, cand_idx);
+}
+
+int y4_forward_heads(y4_engine* e, const float* imgs, int32_t batch, float* hs, float* hm, float* hl) {
+    int rc = ready(e, batch, true); if (rc) return rc;
+    if (!imgs) return fail(e, Y4_ERR_ARG, "null imgs");
+    const size_t n = (size_t)batch * e->cfg.img_size * e->cfg.img_size * 3;
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_img, imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    rc = run_forward(e, batch); if (rc) return rc;
+    float* outs[3] = {hs, hm, hl};
+    const int C = 3 * (5 + e->cfg.num_classes);
+    for (int i = 0; i < 3; i++) {
+        if (!outs[i]) continue;
+        long long total = (long long)batch * e->g[i] * e->g[i] * C;
+        gather_view_kernel<float><<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(
+            (const float*)e->bufs[e->head_buf[i]].ptr, e->d_user_heads[i], batch, e->g[i], e->g[i], C, e->head_ld, 0);
+        e->launches++;
+        CUDA_TRY(e, cudaMemcpyAsync(outs[i], e->d_user_heads[i], total * sizeof(float), cudaMemcpyDeviceToHost, e->stream));
+    }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return Y4_OK;
+}
+
+int y4_decode_nms(y4_engine* e, const float* hs, const float* hm, const float* hl, int32_t batch, float iou_thr,
+                  float score_thr, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx) {
+    int rc = ready(e, batch, false); if (rc) return rc;
+    const float* ins[3] = {hs, hm, hl};
+    const int C = 3 * (5 + e->cfg.num_classes);
+    for (int i = 0; i < 3; i++) {
+        if (!ins[i]) return fail(e, Y4_ERR_ARG, "null head tensor");
+        CUDA_TRY(e, cudaMemcpyAsync(e->d_user_heads[i], ins[i], sizeof(float) * batch * e->g[i] * e->g[i] * C,
+                                    cudaMemcpyHostToDevice, e->stream));
+    }
+    rc = run_decode_nms(e, batch, iou_thr, score_thr, e->d_user_heads); if (rc) return rc;
+    return fetch(e, batch, boxes, scores, classes, valid, cand_idx);
+}
+
+int y4_synth_fill(y4_engine* e, uint64_t seed, int64_t first_index, int32_t batch) {
+    int rc = ready(e, batch, false); if (rc) return rc;
+    const long long per = (long long)e->cfg.img_size * e->cfg.img_size * 3;
+    synth_fill_kernel<<<148 * 8, 256, 0, e->stream>>>(e->d_img, seed, (uint64_t)first_index * (uint64_t)per, per * batch);
+    e->launches++;
+    CUDA_TRY(e, cudaGetLastError());
+    return Y4_OK;
+}
+
+int y4_run_forward_resident(y4_engine* e, int32_t batch) {
+    int rc = ready(e, batch, true); if (rc) return rc;
+    return run_forward(e, batch);
+}
+int y4_run_decode_nms_resident(y4_engine* e, int32_t batch) {
+    int rc = ready(e, batch, false); if (rc) return rc;
+    return run_decode_nms(e, batch, e->cfg.iou_threshold, e->cfg.score_threshold, nullptr);
+}
+int y4_run_resident(y4_engine* e, int32_t batch) {
+    int rc = y4_run_forward_resident(e, batch); if (rc) return rc;
+    return y4_run_decode_nms_resident(e, batch);
+}
+
+int y4_upload_heads(y4_engine* e, const float* hs, const float* hm, const float* hl, int32_t batch) {
+    int rc = ready(e, batch, false); if (rc) return rc;
+    const float* ins[3] = {hs, hm, hl};
+    const int C = 3 * (5 + e->cfg.num_classes);
+    for (int i = 0; i < 3; i++) {
+        if (!ins[i]) return fail(e, Y4_ERR_ARG, "null head tensor");
+        long long total = (long long)batch * e->g[i] * e->g[i] * C;
+        CUDA_TRY(e, cudaMemcpyAsync(e->d_user_heads[i], ins[i], total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+        scatter_head_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(
+            e->d_user_heads[i], (float*)e->bufs[e->head_buf[i]].ptr, batch, e->g[i], C, e->head_ld);
+        e->launches++;
+    }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return Y4_OK;
+}
+
+int y4_fetch_results(y4_engine* e, int32_t batch, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx) {
+    int rc = ready(e, batch, false); if (rc) return rc;
+    return fetch(e, batch, boxes, scores, classes, valid, cand_idx);
+}
+
+int y4_sync(y4_engine* e) {
+    if (!e) return Y4_ERR_ARG;
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return Y4_OK;
+}
+int y4_timer_begin(y4_engine* e) {
+    if (!e) return Y4_ERR_ARG;
+    CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+    return Y4_OK;
+}
+int y4_timer_end(y4_engine* e, float* ms) {
+    if (!e || !ms) return Y4_ERR_ARG;
+    CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+    CUDA_TRY(e, cudaEventSynchronize(e->ev1));
+    CUDA_TRY(e, cudaEventElapsedTime(ms, e->ev0, e->ev1));
+    return Y4_OK;
+}
+int y4_flush_l2(y4_engine* e) {
+    if (!e) return Y4_ERR_ARG;
+    l2_flush_kernel<<<148 * 8, 256, 0, e->stream>>>(e->d_flush, (long long)e->flush_elems, 1.0f);
+    CUDA_TRY(e, cudaGetLastError());
+    return Y4_OK;
+}
+int64_t y4_launch_count(const y4_engine* e) { return e ? e->launches : 0; }
+
+int y4_profile_layers(y4_engine* e, int32_t batch, float* ms, int32_t n) {
+    int rc = ready(e, batch, true); if (rc) return rc;
+    if (!ms || n < (int)e->steps.size()) return fail(e, Y4_ERR_ARG, "ms buffer too small");
+    std::vector<cudaEvent_t> ev(e->steps.size() + 1);
+    for (auto& x : ev) cudaEventCreate(&x);
+    cudaEventRecord(ev[0], e->stream);
+    for (size_t i = 0; i < e->steps.size(); i++) {
+        auto& s = e->steps[i];
+        if (s.type == 0) { rc = run_conv(e, e->convs[s.conv], batch); if (rc) return rc; }
+        else launch_spp(e, batch);
+        cudaEventRecord(ev[i + 1], e->stream);
+    }
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    for (size_t i = 0; i < e->steps.size(); i++) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (auto& x : ev) cudaEventDestroy(x);
+    return (int)e->steps.size();
+}
+
+void* y4_host_alloc(size_t nbytes) { void* p = nullptr; return cudaHostAlloc(&p, nbytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
+void y4_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int y4_num_layers(const y4_engine* e) { return e ? (int)e->convs.size() : 0; }
+int64_t y4_num_boxes(const y4_engine* e) { return e ? e->N : 0; }
+
+int y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info) {
+    if (!e || !info || idx < 0 || idx >= (int)e->convs.size()) return Y4_ERR_ARG;
+    const ConvOp& c = e->convs[idx];
+    info->idx = c.idx; info->cin = c.cin; info->cout = c.cout; info->ksize = c.k; info->stride = c.stride;
+    info->batch_norm = c.bn; info->activation = c.act; info->out_hw = c.N_OH; info->kernel_kind = c.kind;
+    info->tile_n = c.kind ? c.tc.tile_n : 0;
+    info->flops = 2ll * c.N_OH * c.N_OH * c.cout * c.K;
+    snprintf(info->out_name, sizeof(info->out_name), "%s", c.out_name.c_str());
+    return Y4_OK;
+}
+
+int y4_debug_run_conv(y4_engine* e, int32_t idx, int32_t batch, int32_t use_tc) {
+    int rc = ready(e, batch, true); if (rc) return rc;
+    if (idx < 0 || idx >= (int)e->convs.size()) return fail(e, Y4_ERR_ARG, "bad conv idx");
+    const ConvOp& c = e->convs[idx];
+    if (use_tc) {
+        if (c.kind == 0) return fail(e, Y4_ERR_ARG, "conv has no tcgen05 plan");
+        rc = run_conv(e, c, batch); if (rc) return rc;
+    } else {
+        launch_simt(e, c, batch);
+    }
+    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return Y4_OK;
+}
+
+int64_t y4_debug_get_tensor(y4_engine* e, const char* name, int32_t batch, float* out, int64_t capacity) {
+    if (!e || !name) return Y4_ERR_ARG;
+    int rc = check_batch(e, batch); if (rc) return rc;
+    auto it = e->views.find(name);
+    if (it == e->views.end() || it->second.buf < 0) return fail(e, Y4_ERR_ARG, std::string("unknown tensor ") + name);
+    const View& v = it->second;
+    const Buf& b = e->bufs[v.buf];
+    long long total = (long long)batch * v.H * v.W * v.C;
+    if (!out) return total;
+    if (capacity < total) return fail(e, Y4_ERR_ARG, "capacity too small");
+    cudaSetDevice(e->cfg.device);
+    float* tmp = nullptr;
+    CUDA_TRY(e, cudaMalloc(&tmp, total * sizeof(float)));
+    unsigned blocks = (unsigned)((total + 255) / 256);
+    if (b.elt == 4) gather_view_kernel<float><<<blocks, 256, 0, e->stream>>>((const float*)b.ptr, tmp, batch, v.H, v.W, v.C, b.C, v.choff);
+    else gather_view_kernel<__half><<<blocks, 256, 0, e->stream>>>((const __half*)b.ptr, tmp, batch, v.H, v.W, v.C, b.C, v.choff);
+    cudaError_t err = cudaMemcpyAsync(out, tmp, total * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
+    cudaFree(tmp);
+    if (err != cudaSuccess) return fail(e, Y4_ERR_CUDA, cudaGetErrorString(err));
+    return total;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------
+int y4_comm_unique_id(void* uid128) {
+    if (!uid128) return Y4_ERR_ARG;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    if (ncclGetUniqueId(&id) != ncclSuccess) return Y4_ERR_COMM;
+    memcpy(uid128, &id, 128);
+    return Y4_OK;
+}
+
+int y4_comm_init(y4_engine* e, int32_t rank, int32_t nranks, const void* uid128) {
+    if (!e || !uid128 || nranks < 1 || rank < 0 || rank >= nranks) return e ? fail(e, Y4_ERR_ARG, "bad comm args") : Y4_ERR_ARG;
+    cudaSetDevice(e->cfg.device);
+    ncclUniqueId id; memcpy(&id, uid128, 128);
+    ncclResult_t r = ncclCommInitRank(&e->comm, nranks, id, rank);
+    if (r != ncclSuccess) return fail(e, Y4_ERR_COMM, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    e->rank = rank; e->nranks = nranks;
+    const int mb = e->cfg.max_boxes;
+    e->gather_bytes = (size_t)nranks * e->cfg.max_batch * (sizeof(float) * 6 * mb + sizeof(int) * (mb + 1));
+    CUDA_TRY(e, cudaMalloc(&e->d_gather, e->gather_bytes));
+    return Y4_OK;
+}
+
+int y4_allgather_results(y4_engine* e, int32_t batch, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx) {
+    int rc = ready(e, batch, false); if (rc) return rc;
+    if (!e->comm) return fail(e, Y4_ERR_STATE, "y4_comm_init not called");
+    const int mb = e->cfg.max_boxes, R = e->nranks;
+    char* g = static_cast<char*>(e->d_gather);
+    float* gb = reinterpret_cast<float*>(g);                       g += sizeof(float) * 4 * mb * batch * R;
+    float* gs = reinterpret_cast<float*>(g);                       g += sizeof(float) * mb * batch * R;
+    float* gc = reinterpret_cast<float*>(g);                       g += sizeof(float) * mb * batch * R;
+    int* gv = reinterpret_cast<int*>(g);                           g += sizeof(int) * batch * R;
+    int* gi = reinterpret_cast<int*>(g);
+    ncclResult_t r = ncclGroupStart();
+    if (r == ncclSuccess) r = ncclAllGather(e->d_out_boxes, gb, (size_t)4 * mb * batch, ncclFloat, e->comm, e->stream);
+    if (r == ncclSuccess) r = ncclAllGather(e->d_out_scores, gs, (size_t)mb * batch, ncclFloat, e->comm, e->stream);
+    if (r == ncclSuccess) r = ncclAllGather(e->d_out_classes, gc, (size_t)mb * batch, ncclFloat, e->comm, e->stream);
+    if (r == ncclSuccess) r = ncclAllGather(e->d_out_valid, gv, (size_t)batch, ncclInt32, e->comm, e->stream);
+    if (r == ncclSuccess) r = ncclAllGather(e->d_out_idx, gi, (size_t)mb * batch, ncclInt32, e->comm, e->stream);
+    if (r == ncclSuccess) r = ncclGroupEnd();
+    if (r != ncclSuccess) return fail(e, Y4_ERR_COMM, std::string("ncclAllGather: ") + ncclGetErrorString(r));
+    const size_t nb = (size_t)batch * R;
+    if (boxes) CUDA_TRY(e, cudaMemcpyAsync(boxes, gb, sizeof(float) * 4 * mb * nb, cudaMemcpyDeviceToHost, e->stream));
+    if (scores) CUDA_TRY(e, cudaMemcpyAsync(scores, gs, sizeof(float) * mb * nb, cudaMemcpyDeviceToHost, e->stream));
+    if (classes) CUDA_TRY(e, cudaMemcpyAsync(classes, gc, sizeof(float) * mb * nb, cudaMemcpyDeviceToHost, e->stream));
+    if (valid) CUDA_TRY(e, cudaMemcpyAsync(valid, gv, sizeof(int) * nb, cudaMemcpyDeviceToHost, e->stream));
+    if (cand_idx) CUDA_TRY(e, cudaMemcpyAsync(cand_idx, gi, sizeof(int) * mb * nb, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return Y4_OK;
+}
+
+}  // extern "C"
