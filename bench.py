@@ -1,0 +1,251 @@
+#!/usr/bin/env python
+"""bench.py — 608x608 images/sec of the YOLOv4 hot path (110-conv forward + head decode + per-class NMS).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--size 608] [--batch 32]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...      (one rank per GPU, weak scaling)
+
+One "step" = one pass of the hot path over one batch (BASELINE.json configs[1]: batch 32, 608x608, fp16 tensor
+cores, 1xB200).  `value` times K steps with the inputs resident in HBM (CUDA events on the engine stream, max
+over ranks); `e2e` times the same metric through the C-ABI call y4_predict() with pinned HOST buffers (H2D of
+the images and D2H of the detections inside the timed region).  `roofline` is the conv stack (tcgen05 kernels):
+algorithmic conv FLOPs per step / its CUDA-event duration, against the measured dense-bf16 peak.
+`--impl reference` times the CPU restatement of the reference (oracle/, numpy + BLAS, all host threads) on a
+bounded sample of the same workload: TensorFlow is not installable in this image, so the reference's own
+tf.keras CPU forward cannot be run.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, 'oracle')):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = '608x608 images/sec'
+
+
+def conv_gflop(size):
+    import netspec
+    return netspec.conv_gflop(size)
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {'tflops': float(p.get('bf16_tflops_sustained', p.get('bf16_tflops'))), 'hbm_gbs': float(p['hbm_gbs']),
+                'source': 'MEASURED_PEAKS.json (bf16_tflops_sustained: kernel timed inside a long step)'}
+    return {'tflops': 1400.0, 'hbm_gbs': 6650.0, 'source': 'fallback (B200_PROFILING.md: 1.4 PF sustained, 6.65 TB/s)'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.device), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+def cpu_port_images_per_sec(size, n_images, weights):
+    """The oracle (CPU restatement of the reference, numpy + multithreaded BLAS) on a bounded sample."""
+    import y4_oracle as O
+    imgs = O.synth_images(0, 0, n_images, size)
+    t0 = time.perf_counter()
+    O.predict(imgs, weights)
+    dt = time.perf_counter() - t0
+    return n_images / dt, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; TF unavailable here)."""
+    if rank != 0:
+        return
+    import y4_oracle as O
+    cores = len(os.sched_getaffinity(0))
+    W = O.synth_weights(seed=1)
+    sample = 1                                   # images per step: bounded so K steps end within minutes
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_images_per_sec(args.size, sample, W)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_port_images_per_sec(args.size, sample, W)
+    dt = time.perf_counter() - t0
+    v = args.steps * sample / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'images/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'yolov4 forward+decode+nms {args.size}x{args.size}, {sample} image/step (bounded sample of batch {args.batch})'},
+            'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                             'sample': f'{sample} image per step x {args.steps} steps, numpy+OpenBLAS oracle (tf.keras not installable)'},
+            'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--size', type=int, default=608)
+    ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist       # host-side rendezvous only (uid broadcast, barrier, max-reduce)
+        dist.init_process_group('gloo', rank=rank, world_size=world)
+
+    import y4b200
+    import y4_oracle as O
+    from y4b200 import binding
+
+    S, B = args.size, args.batch
+    prec = y4b200.PREC_FP16 if args.precision == 'fp16' else y4b200.PREC_FP32
+    eng = y4b200.Engine(img_size=S, max_batch=B, precision=prec, device=local)
+    W = O.synth_weights(seed=1)
+    eng.load_darknet_bytes(W.to_darknet_bytes())
+    if world > 1:
+        import torch
+        uid = torch.from_numpy(eng.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8))
+        dist.broadcast(uid, 0)
+        eng.comm_init(rank, world, uid.numpy())
+
+    def barrier():
+        eng.sync()
+        if dist is not None:
+            dist.barrier()
+
+    def step_resident():
+        eng.run_resident(B)
+        if world > 1:
+            eng.allgather_results(B, fetch=False)
+
+    # ---- resident timing: value -------------------------------------------------------------------
+    eng.synth_fill(0, rank * B, B)                     # image i depends only on its global index
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = eng.launch_count()
+    eng.timer_begin()
+    for _ in range(args.steps):
+        step_resident()
+    ms = eng.timer_end()
+    launches = eng.launch_count() - l0
+    barrier()
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_per_step = ms / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---- conv stack alone: roofline numerator -----------------------------------------------------
+    eng.timer_begin()
+    for _ in range(args.steps):
+        eng.run_forward_resident(B)
+    fwd_ms = eng.timer_end() / args.steps
+    eng.timer_begin()
+    for _ in range(args.steps):
+        eng.run_decode_nms_resident(B)
+    dn_ms = eng.timer_end() / args.steps
+    clk = clocks.stop()
+    pk = peaks()
+    gflop_step = conv_gflop(S) * B
+    achieved = gflop_step / fwd_ms                     # GFLOP/ms == TFLOP/s
+    roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
+                'traffic': None, 'kernel': 'conv_tc_kernel (109 tcgen05 conv launches + conv0 + SPP per step)',
+                'flops_per_step': gflop_step * 1e9, 'forward_ms_per_step': fwd_ms, 'peak_source': pk['source']}
+
+    # ---- e2e through the C-ABI with host buffers --------------------------------------------------
+    imgs = binding.pinned_array((B, S, S, 3))
+    imgs[...] = O.synth_images(0, rank * B, B, S)
+    e2e_steps = max(3, min(args.steps, 10))
+    eng.predict(imgs)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = eng.predict(imgs)
+    barrier()
+    e2e_dt = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_dt], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dt = float(t.item())
+    mb = eng.max_boxes
+    e2e = {'value': world * B * e2e_steps / e2e_dt, 'unit': 'images/s', 'h2d_bytes_per_step': int(imgs.nbytes),
+           'd2h_bytes_per_step': int(B * (mb * 4 * 4 + mb * 4 + mb * 4 + 4)), 'steps': e2e_steps,
+           'api': 'y4_predict (host float32 NHWC in, detections out)'}
+
+    if rank != 0:
+        return
+    line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f16' if args.precision == 'fp16' else 'f32', 'data': 'synthetic',
+            'config': {'workload': f'configs[1]: yolov4 CSPDarknet53+SPP+PANet forward + 3-scale decode + per-class NMS, '
+                                   f'batch {B}/GPU, {S}x{S}, 80 classes, seeded random weights/images',
+                       'l2': 'activations written+read per step (~7.3 GB at batch 32) >> 126 MB L2; no flush needed',
+                       'global_batch': world * B, 'parallelism': f'dp{world}'},
+            'gpu_launches': launches, 'clocks': clk, 'e2e': e2e, 'roofline': roofline,
+            'decode_nms_us_per_img': 1e3 * dn_ms / B, 'valid_detections_img0': int(out[3][0])}
+    if not args.no_cpu_baseline:
+        cores = len(os.sched_getaffinity(0))
+        v, dt = cpu_port_images_per_sec(S, 2, W)
+        line['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
+                                'sample': f'2 images {S}x{S} through the numpy+OpenBLAS oracle ({dt:.1f} s); tf.keras itself is not installable here'}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == '__main__':
+    main()

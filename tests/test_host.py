@@ -1,0 +1,78 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/y4.h declares; host-side mirror of the
+reference API (config, get_detection_data) behaves like the reference code paths it replaces."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported():
+    from y4b200 import binding
+    lib = binding.load_library()
+    hdr = open(os.path.join(ROOT, 'include', 'y4.h')).read()
+    declared = set(re.findall(r'\b(y4_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(binding.EXPORTS), declared ^ set(binding.EXPORTS)
+
+
+def test_no_gpu_fails_loudly():
+    """No CPU fallback: without a usable sm_100 device y4_create must fail with Y4_ERR_CUDA."""
+    import ctypes as C
+    import y4b200
+    from y4b200 import binding
+    lib = binding.load_library()
+    cfg = binding.Y4Config()
+    assert lib.y4_default_config(C.byref(cfg)) == 0
+    assert (cfg.img_size, cfg.num_classes, cfg.max_boxes) == (416, 80, 100)
+    assert list(cfg.strides) == [8, 16, 32] and list(cfg.xyscale) == [1.2, 1.1, 1.05]
+    assert abs(cfg.iou_threshold - 0.413) < 1e-7 and abs(cfg.score_threshold - 0.3) < 1e-7
+    have_gpu = os.path.exists('/dev/nvidia0')
+    if not have_gpu:
+        with pytest.raises(y4b200.Y4Error) as ei:
+            y4b200.Engine()
+        assert ei.value.code == -2
+    cfg.img_size = 400                                  # not a multiple of 32 (models.py:24)
+    h = C.c_void_p()
+    assert lib.y4_create(C.byref(h), C.byref(cfg)) == -1
+    assert b'multiple' in lib.y4_last_error(None)
+
+
+def test_config_matches_reference_defaults():
+    from y4b200 import yolo_config
+    assert yolo_config['img_size'] == (416, 416, 3)
+    assert yolo_config['anchors'] == [12, 16, 19, 36, 40, 28, 36, 75, 76, 55, 72, 146, 142, 110, 192, 243, 459, 401]
+    assert yolo_config['strides'] == [8, 16, 32] and yolo_config['xyscale'] == [1.2, 1.1, 1.05]
+    assert (yolo_config['max_boxes'], yolo_config['iou_threshold'], yolo_config['score_threshold']) == (100, 0.413, 0.3)
+
+
+def test_get_detection_data_matches_oracle_table():
+    """utils.py:56-78: first image only, int64 truncation, DataFrame columns."""
+    import y4_oracle as O
+    from y4b200.utils import get_detection_data
+    boxes = np.zeros((2, 100, 4), np.float32); scores = np.zeros((2, 100), np.float32)
+    classes = np.zeros((2, 100), np.float32); valid = np.array([2, 0], np.int32)
+    boxes[0, 0] = [0.1017, 0.2049, 0.5551, 0.7999]; boxes[0, 1] = [0.0, 0.3333, 0.9999, 1.0]
+    scores[0, :2] = [0.91, 0.42]; classes[0, :2] = [2, 0]
+    names = ['person', 'bicycle', 'car']
+    img = np.zeros((185, 273, 3), np.uint8)
+    df = get_detection_data(img, [boxes, scores, classes, valid], names)
+    assert list(df.columns) == ['x1', 'y1', 'x2', 'y2', 'class_name', 'score', 'w', 'h']
+    rows = O.detection_table((185, 273), (boxes, scores, classes, valid), names)
+    assert len(df) == 2
+    for i, r in enumerate(rows):
+        assert [int(df.iloc[i][c]) for c in ('x1', 'y1', 'x2', 'y2')] == list(r[:4])
+        assert df.iloc[i]['class_name'] == r[4] and int(df.iloc[i]['w']) == r[6] and int(df.iloc[i]['h']) == r[7]
+    assert df['x1'].dtype == np.int64
+
+
+def test_preprocess_contract():
+    """models.py:95-98: cv2.resize to (S,S) (no letterbox) then /255 -> float64 in [0,1]."""
+    import y4_oracle as O
+    img = (np.arange(30 * 50 * 3) % 256).astype(np.uint8).reshape(30, 50, 3)
+    out = O.preprocess_img(img, 64)
+    assert out.shape == (64, 64, 3) and out.dtype == np.float64 and 0 <= out.min() and out.max() <= 1

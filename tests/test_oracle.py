@@ -1,0 +1,198 @@
+"""CPU tests (-m "not gpu"): the oracle against independent implementations and the reference's structural
+known-answers (the reference has no tests and no replayable golden vector -> parity unpinned)."""
+import numpy as np
+import pytest
+
+import netspec
+import y4_oracle as O
+
+
+def test_netlist_known_answers():
+    # utils.py:13-14: conv_layer_size = 110, conv_output_idxs = [93, 101, 109]
+    cs = netspec.conv_ops()
+    assert len(cs) == 110
+    assert [c.idx for c in cs if not c.bn] == [93, 101, 109]
+    assert all(c.act == 'linear' and c.cout == 255 for c in cs if not c.bn)
+    # darknet yolov4.weights size implied by utils.py:16-41
+    assert 20 + 4 * netspec.darknet_file_floats() == 257717640
+    # census: 70 mish / 37 leaky / 3 linear; 66 1x1, 37 3x3 s1, 7 3x3 s2; convs 0,1 leaky
+    acts = [c.act for c in cs]
+    assert (acts.count('mish'), acts.count('leaky'), acts.count('linear')) == (70, 37, 3)
+    ks = [(c.k, c.stride) for c in cs]
+    assert (ks.count((1, 1)), ks.count((3, 1)), ks.count((3, 2))) == (66, 37, 7)
+    assert cs[0].act == cs[1].act == 'leaky'
+    for s, gf in ((320, 35.565), (416, 60.105), (512, 91.046), (608, 128.389), (768, 204.854)):
+        assert abs(netspec.conv_gflop(s) - gf) < 1e-3
+    ops, heads = netspec.build_netlist()
+    cat = {o.out: o.ins for o in ops if o.kind == 'concat'}
+    assert cat['cat1'] == ['c6', 'c2'] and cat['cat6'] == ['mp13', 'mp9', 'mp5', 'c74']      # main first, route second
+    assert cat['cat7'] == ['c79', 'up_c78'] and cat['cat10'] == ['c102', 'c77']
+    assert heads == ['c93', 'c101', 'c109']
+
+
+def test_conv_against_torch():
+    torch = pytest.importorskip('torch')
+    F = torch.nn.functional
+    rng = np.random.default_rng(0)
+    for (cin, cout, k, stride, hw) in ((3, 8, 3, 1, 9), (16, 8, 1, 1, 6), (8, 16, 3, 2, 10), (8, 8, 3, 2, 12)):
+        x = rng.standard_normal((2, hw, hw, cin)).astype(np.float32)
+        w = rng.standard_normal((k, k, cin, cout)).astype(np.float32)
+        got = O.conv2d_raw(x, w, stride)
+        xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+        wt = torch.from_numpy(w).permute(3, 2, 0, 1)
+        if stride == 1:
+            ref = F.conv2d(xt, wt, padding=k // 2)
+        else:                                           # ZeroPadding2D(((1,0),(1,0))) + valid stride 2
+            ref = F.conv2d(F.pad(xt, (1, 0, 1, 0)), wt, stride=2)
+        ref = ref.permute(0, 2, 3, 1).numpy()
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() < 1e-4
+
+
+def test_pool_upsample_act_against_torch():
+    torch = pytest.importorskip('torch')
+    F = torch.nn.functional
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((2, 13, 13, 6)).astype(np.float32)
+    xt = torch.from_numpy(x).permute(0, 3, 1, 2)
+    for k in (5, 9, 13):
+        ref = F.max_pool2d(xt, k, stride=1, padding=k // 2).permute(0, 2, 3, 1).numpy()
+        assert np.array_equal(O.maxpool_same(x, k), ref)
+    assert np.array_equal(O.maxpool_same(O.maxpool_same(x, 5), 5), O.maxpool_same(x, 9))     # cascade identity
+    ref = F.interpolate(xt, scale_factor=2, mode='nearest').permute(0, 2, 3, 1).numpy()
+    assert np.array_equal(O.upsample2x(x), ref)
+    v = np.linspace(-30, 30, 601).astype(np.float32)
+    assert np.abs(O.mish(v) - F.mish(torch.from_numpy(v)).numpy()).max() < 1e-5
+    assert np.abs(O.leaky(v) - F.leaky_relu(torch.from_numpy(v), 0.1).numpy()).max() == 0
+
+
+def test_darknet_roundtrip_and_size_check(weights):
+    W, blob = weights
+    assert len(blob) == 257717640
+    W2 = O.Weights.from_darknet_bytes(blob)
+    for a, b in zip(W.p, W2.p):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k])
+    with pytest.raises(ValueError):
+        O.Weights.from_darknet_bytes(blob[:-4])
+    # darknet order [beta, gamma, mean, var] then OIHW (utils.py:29-42): first conv's BN block sits right after the header
+    beta0 = np.frombuffer(blob, '<f4', 32, 20)
+    assert np.array_equal(beta0, W.p[0]['beta'])
+    w0 = np.frombuffer(blob, '<f4', 32 * 3 * 9, 20 + 4 * 32 * 4).reshape(32, 3, 3, 3)
+    assert np.array_equal(w0.transpose(2, 3, 1, 0), W.p[0]['w'])
+
+
+def test_decode_matches_reference_formulas():
+    """get_boxes (custom_layers.py:221-258) re-derived per element in float64."""
+    rng = np.random.default_rng(2)
+    g, nc, stride, xs = 4, 3, 16, 1.1
+    pred = rng.standard_normal((1, g, g, 3 * (5 + nc))).astype(np.float32)
+    box, obj, cls = O.get_boxes(pred, O.ANCHORS[1], nc, g, stride, xs)
+    p = pred.reshape(1, g, g, 3, 5 + nc).astype(np.float64)
+    for r in range(g):
+        for c in range(g):
+            for a in range(3):
+                sx, sy = 1 / (1 + np.exp(-p[0, r, c, a, 0])), 1 / (1 + np.exp(-p[0, r, c, a, 1]))
+                bx = (sx * xs - 0.5 * (xs - 1) + c) * stride          # grid[...,0] = column
+                by = (sy * xs - 0.5 * (xs - 1) + r) * stride
+                bw = np.exp(p[0, r, c, a, 2]) * O.ANCHORS[1][a, 0]
+                bh = np.exp(p[0, r, c, a, 3]) * O.ANCHORS[1][a, 1]
+                ref = [bx - bw / 2, by - bh / 2, bx + bw / 2, by + bh / 2]
+                assert np.abs(box[0, r, c, a] - ref).max() < 1e-3
+    assert np.abs(obj[..., 0] - 1 / (1 + np.exp(-p[..., 4]))).max() < 1e-6
+    # flat index order: n = (row*g + col)*3 + a  (custom_layers.py:274-280)
+    boxes, scores = O.decode_heads([np.zeros((1, 8, 8, 24), np.float32), pred, np.zeros((1, 2, 2, 24), np.float32)], 64, nc)
+    n = 3 * 64 + (2 * g + 1) * 3 + 2
+    assert np.allclose(boxes[0, n] * 64, box[0, 2, 1, 2], atol=1e-4)
+    assert np.allclose(scores[0, n], obj[0, 2, 1, 2] * cls[0, 2, 1, 2])
+
+
+def _brute_nms(boxes, scores, iou_thr, score_thr, max_per_class, max_total):
+    """Independent restatement: vectorised IoU matrix + greedy scan."""
+    out = []
+    B, N, C = scores.shape
+    for b in range(B):
+        bb = boxes[b].astype(np.float32)
+        y0, y1 = np.minimum(bb[:, 0], bb[:, 2]), np.maximum(bb[:, 0], bb[:, 2])
+        x0, x1 = np.minimum(bb[:, 1], bb[:, 3]), np.maximum(bb[:, 1], bb[:, 3])
+        area = ((y1 - y0) * (x1 - x0)).astype(np.float32)
+        picked = []
+        for c in range(C):
+            idx = np.nonzero(scores[b, :, c] > np.float32(score_thr))[0]
+            idx = idx[np.lexsort((idx, -scores[b, idx, c].astype(np.float64)))]
+            keep = []
+            for i in idx:
+                ok = True
+                for j in keep:
+                    ih = np.float32(max(np.float32(min(y1[i], y1[j]) - max(y0[i], y0[j])), 0))
+                    iw = np.float32(max(np.float32(min(x1[i], x1[j]) - max(x0[i], x0[j])), 0))
+                    inter = np.float32(ih * iw)
+                    iou = np.float32(0) if area[i] <= 0 or area[j] <= 0 else np.float32(inter / np.float32(np.float32(area[i] + area[j]) - inter))
+                    if iou > np.float32(iou_thr):
+                        ok = False
+                        break
+                if ok:
+                    keep.append(i)
+                    if len(keep) == max_per_class:
+                        break
+            picked += [(-float(scores[b, i, c]), c, int(i)) for i in keep]
+        picked.sort()
+        out.append(picked[:max_total])
+    return out
+
+
+def test_nms_against_bruteforce():
+    for seed, size in ((1, 128), (2, 160)):
+        heads = O.synth_heads(seed, 2, size, n_clusters=25)
+        boxes, scores = O.decode_heads(heads, size)
+        rb, rs, rc, rv, ri = O.combined_nms(boxes, scores)
+        ref = _brute_nms(boxes, scores, O.IOU_THRESHOLD, O.SCORE_THRESHOLD, 100, 100)
+        for b in range(2):
+            assert rv[b] == len(ref[b])
+            assert [int(i) for i in ri[b, :rv[b]]] == [t[2] for t in ref[b]]
+            assert [int(c) for c in rc[b, :rv[b]]] == [t[1] for t in ref[b]]
+            assert np.all(np.diff(rs[b, :rv[b]]) <= 0)
+            assert (rb[b] >= 0).all() and (rb[b] <= 1).all()
+            assert not rb[b, rv[b]:].any() and (ri[b, rv[b]:] == -1).all()
+
+
+def test_nms_semantics_edge_cases():
+    # two identical boxes, same class: second suppressed (iou 1 > thr); different class: both kept
+    boxes = np.array([[[0.1, 0.1, 0.5, 0.5], [0.1, 0.1, 0.5, 0.5], [0.6, 0.6, 0.9, 0.9]]], np.float32)
+    scores = np.zeros((1, 3, 2), np.float32)
+    scores[0, 0, 0], scores[0, 1, 0], scores[0, 2, 1] = 0.9, 0.8, 0.7
+    rb, rs, rc, rv, ri = O.combined_nms(boxes, scores)
+    assert rv[0] == 2 and ri[0, :2].tolist() == [0, 2] and rc[0, :2].tolist() == [0, 1]
+    scores[0, 1, 0], scores[0, 1, 1] = 0, 0.8
+    assert O.combined_nms(boxes, scores)[3][0] == 3
+    # strict '>' on the score threshold; clip on output only; degenerate (zero-area) boxes never suppress
+    scores[:] = 0; scores[0, 0, 0] = np.float32(0.3)
+    assert O.combined_nms(boxes, scores)[3][0] == 0
+    boxes2 = np.array([[[-0.2, 0.2, 1.3, 0.8], [0.4, 0.4, 0.4, 0.9]]], np.float32)
+    sc2 = np.array([[[0.9], [0.8]]], np.float32)
+    rb, rs, rc, rv, ri = O.combined_nms(boxes2, sc2)
+    assert rv[0] == 2 and rb[0, 0].tolist() == pytest.approx([0, 0.2, 1, 0.8])
+    # empty input
+    rv = O.combined_nms(np.zeros((1, 0, 4), np.float32), np.zeros((1, 0, 3), np.float32))[3]
+    assert rv[0] == 0
+
+
+def test_synth_images_shard_invariance():
+    a = O.synth_images(3, 0, 4, 32)
+    b = np.concatenate([O.synth_images(3, 0, 2, 32), O.synth_images(3, 2, 2, 32)])
+    assert np.array_equal(a, b) and a.dtype == np.float32 and 0 <= a.min() and a.max() < 1
+
+
+def test_oracle_predict_small(weights):
+    W, _ = weights
+    imgs = O.synth_images(0, 0, 1, 96)
+    m = {}
+    boxes, scores, classes, valid, idx = O.predict(imgs, W, margins=m)
+    assert boxes.shape == (1, 100, 4) and scores.shape == (1, 100) and valid.shape == (1,)
+    n = 3 * (12 * 12 + 6 * 6 + 3 * 3)
+    assert (idx[0, :valid[0]] < n).all()
+    heads = O.forward(imgs, W)
+    heads_f = O.forward(imgs, W, fold_bn=True)
+    for a, b in zip(heads, heads_f):                    # BN folding is exact up to fp32 round-off
+        assert np.abs(a - b).max() / np.abs(a).max() < 1e-4

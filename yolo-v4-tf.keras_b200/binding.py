@@ -278,7 +278,10 @@ class Engine:
         self._chk(self._lib.y4_comm_init(self._h, rank, nranks, _ptr(uid)))
         self.nranks = nranks
 
-    def allgather_results(self, batch):
+    def allgather_results(self, batch, fetch=True):
+        if not fetch:        # enqueue the NCCL all-gather only (device-resident, async on the engine stream)
+            self._chk(self._lib.y4_allgather_results(self._h, batch, None, None, None, None, None))
+            return None
         mb, R = self.max_boxes, self.nranks
         out = (np.zeros((R * batch, mb, 4), np.float32), np.zeros((R * batch, mb), np.float32),
                np.zeros((R * batch, mb), np.float32), np.zeros((R * batch,), np.int32), np.zeros((R * batch, mb), np.int32))

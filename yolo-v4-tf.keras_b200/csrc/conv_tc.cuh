@@ -82,8 +82,10 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
 }
 // Bounded spin: a pipeline bug traps (launch failure the host reports) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t i = 0; !mbar_try(bar, parity); ++i)
-        if (i > (1u << 26)) __trap();
+    if (mbar_try(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try(bar, parity))
+        if (clock64() - t0 > 4000000000ll) __trap();       // ~2 s at 1.9 GHz: orders of magnitude beyond any legal wait
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(

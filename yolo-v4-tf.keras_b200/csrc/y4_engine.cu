@@ -10,7 +10,9 @@
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cuda.h>
-#include <nccl.h>
+#include <nccl.h>   // types only: the library is dlopen()ed lazily (see NcclApi) so that liby4.so never pins a
+                    // libnccl.so.2 before a host process (e.g. torch) loads its own
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -98,6 +100,37 @@ struct y4_engine {
 };
 
 namespace {
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);      // an already-loaded libnccl.so.2 (torch's) is reused
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+            api.GroupStart = (decltype(api.GroupStart))dlsym(h, "ncclGroupStart");
+            api.GroupEnd = (decltype(api.GroupEnd))dlsym(h, "ncclGroupEnd");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GroupStart && api.GroupEnd && api.GetErrorString;
+        }
+    }
+    return api;
+}
 
 int fail(y4_engine* e, int code, const std::string& msg) {
     if (e) e->err = msg; else g_create_error = msg;
@@ -561,7 +594,7 @@ void y4_destroy(y4_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    if (e->comm) ncclCommDestroy(e->comm);
+    if (e->comm) nccl().CommDestroy(e->comm);
     for (auto& b : e->bufs) cudaFree(b.ptr);
     for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_bias); }
     cudaFree(e->d_img);
@@ -793,7 +826,8 @@ int y4_comm_unique_id(void* uid128) {
     if (!uid128) return Y4_ERR_ARG;
     static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
     ncclUniqueId id;
-    if (ncclGetUniqueId(&id) != ncclSuccess) return Y4_ERR_COMM;
+    if (!nccl().ok) return fail(nullptr, Y4_ERR_COMM, "libnccl.so.2 could not be loaded");
+    if (nccl().GetUniqueId(&id) != ncclSuccess) return Y4_ERR_COMM;
     memcpy(uid128, &id, 128);
     return Y4_OK;
 }
@@ -802,8 +836,9 @@ int y4_comm_init(y4_engine* e, int32_t rank, int32_t nranks, const void* uid128)
     if (!e || !uid128 || nranks < 1 || rank < 0 || rank >= nranks) return e ? fail(e, Y4_ERR_ARG, "bad comm args") : Y4_ERR_ARG;
     cudaSetDevice(e->cfg.device);
     ncclUniqueId id; memcpy(&id, uid128, 128);
-    ncclResult_t r = ncclCommInitRank(&e->comm, nranks, id, rank);
-    if (r != ncclSuccess) return fail(e, Y4_ERR_COMM, std::string("ncclCommInitRank: ") + ncclGetErrorString(r));
+    if (!nccl().ok) return fail(e, Y4_ERR_COMM, "libnccl.so.2 could not be loaded");
+    ncclResult_t r = nccl().CommInitRank(&e->comm, nranks, id, rank);
+    if (r != ncclSuccess) return fail(e, Y4_ERR_COMM, std::string("ncclCommInitRank: ") + nccl().GetErrorString(r));
     e->rank = rank; e->nranks = nranks;
     const int mb = e->cfg.max_boxes;
     e->gather_bytes = (size_t)nranks * e->cfg.max_batch * (sizeof(float) * 6 * mb + sizeof(int) * (mb + 1));
@@ -821,21 +856,21 @@ int y4_allgather_results(y4_engine* e, int32_t batch, float* boxes, float* score
     float* gc = reinterpret_cast<float*>(g);                       g += sizeof(float) * mb * batch * R;
     int* gv = reinterpret_cast<int*>(g);                           g += sizeof(int) * batch * R;
     int* gi = reinterpret_cast<int*>(g);
-    ncclResult_t r = ncclGroupStart();
-    if (r == ncclSuccess) r = ncclAllGather(e->d_out_boxes, gb, (size_t)4 * mb * batch, ncclFloat, e->comm, e->stream);
-    if (r == ncclSuccess) r = ncclAllGather(e->d_out_scores, gs, (size_t)mb * batch, ncclFloat, e->comm, e->stream);
-    if (r == ncclSuccess) r = ncclAllGather(e->d_out_classes, gc, (size_t)mb * batch, ncclFloat, e->comm, e->stream);
-    if (r == ncclSuccess) r = ncclAllGather(e->d_out_valid, gv, (size_t)batch, ncclInt32, e->comm, e->stream);
-    if (r == ncclSuccess) r = ncclAllGather(e->d_out_idx, gi, (size_t)mb * batch, ncclInt32, e->comm, e->stream);
-    if (r == ncclSuccess) r = ncclGroupEnd();
-    if (r != ncclSuccess) return fail(e, Y4_ERR_COMM, std::string("ncclAllGather: ") + ncclGetErrorString(r));
+    ncclResult_t r = nccl().GroupStart();
+    if (r == ncclSuccess) r = nccl().AllGather(e->d_out_boxes, gb, (size_t)4 * mb * batch, ncclFloat, e->comm, e->stream);
+    if (r == ncclSuccess) r = nccl().AllGather(e->d_out_scores, gs, (size_t)mb * batch, ncclFloat, e->comm, e->stream);
+    if (r == ncclSuccess) r = nccl().AllGather(e->d_out_classes, gc, (size_t)mb * batch, ncclFloat, e->comm, e->stream);
+    if (r == ncclSuccess) r = nccl().AllGather(e->d_out_valid, gv, (size_t)batch, ncclInt32, e->comm, e->stream);
+    if (r == ncclSuccess) r = nccl().AllGather(e->d_out_idx, gi, (size_t)mb * batch, ncclInt32, e->comm, e->stream);
+    if (r == ncclSuccess) r = nccl().GroupEnd();
+    if (r != ncclSuccess) return fail(e, Y4_ERR_COMM, std::string("ncclAllGather: ") + nccl().GetErrorString(r));
     const size_t nb = (size_t)batch * R;
     if (boxes) CUDA_TRY(e, cudaMemcpyAsync(boxes, gb, sizeof(float) * 4 * mb * nb, cudaMemcpyDeviceToHost, e->stream));
     if (scores) CUDA_TRY(e, cudaMemcpyAsync(scores, gs, sizeof(float) * mb * nb, cudaMemcpyDeviceToHost, e->stream));
     if (classes) CUDA_TRY(e, cudaMemcpyAsync(classes, gc, sizeof(float) * mb * nb, cudaMemcpyDeviceToHost, e->stream));
     if (valid) CUDA_TRY(e, cudaMemcpyAsync(valid, gv, sizeof(int) * nb, cudaMemcpyDeviceToHost, e->stream));
     if (cand_idx) CUDA_TRY(e, cudaMemcpyAsync(cand_idx, gi, sizeof(int) * mb * nb, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (boxes || scores || classes || valid || cand_idx) CUDA_TRY(e, cudaStreamSynchronize(e->stream));   // all-NULL: device-side gather only, async
     return Y4_OK;
 }
 
