@@ -40,3 +40,22 @@ def test_tc_vs_simt_per_layer(weights, size, batch):
     report(f'tc_vs_simt_{size}', worst=worst, bad=bad, n=len(errs))
     assert not bad, bad
     eng.close()
+
+
+def test_spp_is_exact_max(weights):
+    """SPP slices (custom_layers.py:130-134) of the fp16 engine == numpy max-pools of the engine's own input slice."""
+    import y4b200
+    import y4_oracle as O
+    W, blob = weights
+    size, batch = 416, 2
+    eng = y4b200.Engine(img_size=size, max_batch=batch, precision=y4b200.PREC_FP16)
+    eng.load_darknet_bytes(blob)
+    eng.forward_heads(O.synth_images(0, 0, batch, size))
+    g = size // 32
+    x = eng.get_tensor('c74', batch).reshape(batch, g, g, 512)
+    for k in (13, 9, 5):
+        got = eng.get_tensor(f'mp{k}', batch).reshape(batch, g, g, 512)
+        assert np.array_equal(got, O.maxpool_same(x, k)), k
+    cat = eng.get_tensor('cat6', batch).reshape(batch, g, g, 2048)
+    assert np.array_equal(cat[..., 1536:], x)
+    eng.close()

@@ -379,9 +379,9 @@ template <int BN, int BK>
 inline cudaError_t launch_inst(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
     static size_t configured = 0;
     if (pl.smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
         if (e != cudaSuccess) return e;
-        configured = 200 * 1024;
+        configured = 220 * 1024;
     }
     conv_tc_kernel<BN, BK><<<grid, kTcThreads, pl.smem, st>>>(pl.p);
     return cudaGetLastError();
@@ -414,14 +414,15 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 }
 
 // returns kernel kind (0 = not eligible -> CUDA-core kernel, 1 = flat GEMM, 2 = strided box), <0 on error
-inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err) {
+inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99) {
     if (d.raw_in) return 0;                                   // conv 0 (cin = 3): CUDA-core kernel
     const int bk = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 0);
     if (!bk) return 0;
     if (d.upsample && d.out_f32) return 0;
     int bn = d.cout_pad >= 128 ? 128 : 64;
-    if (const char* env = getenv("Y4_TC_BN")) { int v = atoi(env); if ((v == 64 || v == 128 || v == 256) && d.cout_pad % v == 0 && !(bk == 32 && v == 256)) bn = v; }
-    if (d.cout_pad % bn) return 0;
+    if (bn_req) bn = bn_req;
+    if (const char* env = getenv("Y4_TC_BN")) { int v = atoi(env); if (v == 64 || v == 128 || v == 256) bn = v; }
+    if (d.cout_pad % bn || (bk == 32 && bn == 256)) { if (bn_req) return 0; bn = d.cout_pad >= 128 ? 128 : 64; }
     TcConvPlan P;
     TcParams& p = P.p;
     memset(&p, 0, sizeof(p));
@@ -478,13 +479,13 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err) {
             }
     }
     const size_t stage_bytes = (size_t)128 * bk * 2 + (size_t)bn * bk * 2;
-    int S = (int)((99 * 1024) / stage_bytes);            // <= ~100 KB so that two CTAs share an SM
+    int S = (int)(((size_t)smem_budget_kb * 1024) / stage_bytes);   // default budget ~100 KB: two CTAs share an SM
     if (S < 2) S = 2;
     if (S > 8) S = 8;
     if (S > p.num_kb) S = p.num_kb;
     P.stages = S; p.stages = S;
     P.smem = 1024 + S * stage_bytes + 16 * S + 16;
-    if (P.smem > 200 * 1024) { *err = "smem budget exceeded"; return -1; }
+    if (P.smem > 220 * 1024) { *err = "smem budget exceeded"; return -1; }
     *pl = P;
     return P.kind;
 }

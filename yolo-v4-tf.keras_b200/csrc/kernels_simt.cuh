@@ -157,12 +157,130 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(SimtConvParams p) {
     }
 }
 
-// SPP (custom_layers.py:130-134): mp13 | mp9 | mp5 | x, stride 1, 'same' (out-of-range cells ignored).
-// One thread per (n,h,w,c): nested windows 5 c 9 c 13 share one sweep.
+// conv 0 (cin = 3, 3x3 'same', leaky) straight from the caller's float32 NHWC image: direct convolution on CUDA
+// cores, fp32 accumulate, fp16 padded-flat output.  A block computes a 32 x 16 pixel tile x 32 channels; each thread
+// owns two pixels (rows y and y+8) so every broadcast weight read feeds two FMAs.  Output rows are 64 B and
+// consecutive lanes write consecutive pixels: fully coalesced 2 KB per warp store.
+struct Conv0Params {
+    const float* img;      // (N, S, S, 3)
+    const float* w;        // [27][cout_pad] folded, K index = (kh*3+kw)*3 + c
+    const float* bias;     // [cout_pad]
+    __half* out;           // padded-flat (N, S+2, S+2, 32)
+    int N, S, cout_pad;
+};
+
+__global__ void __launch_bounds__(256) conv0_direct_kernel(Conv0Params p) {
+    constexpr int TW = 32, TH = 16;
+    __shared__ float patch[TH + 2][(TW + 2) * 3];
+    __shared__ __align__(16) float ws[27][32];
+    __shared__ float bs[32];
+    const int tid = threadIdx.x;
+    const int n = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+    for (int i = tid; i < 27 * 32; i += 256) ws[i >> 5][i & 31] = p.w[(i >> 5) * p.cout_pad + (i & 31)];
+    if (tid < 32) bs[tid] = p.bias[tid];
+    const float* img = p.img + (long long)n * p.S * p.S * 3;
+    for (int i = tid; i < (TH + 2) * (TW + 2) * 3; i += 256) {
+        const int r = i / ((TW + 2) * 3), c = i - r * ((TW + 2) * 3);
+        const int iy = y0 + r - 1, ix3 = x0 * 3 + c - 3;          // column index in floats of the image row
+        float v = 0.f;
+        if (iy >= 0 && iy < p.S && ix3 >= 0 && ix3 < p.S * 3) v = img[(long long)iy * p.S * 3 + ix3];
+        patch[r][c] = v;
+    }
+    __syncthreads();
+    const int tx = tid & 31, ty = tid >> 5;                      // ty in 0..7, pixels (ty, tx) and (ty+8, tx)
+    float a0[32], a1[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) { a0[c] = 0.f; a1[c] = 0.f; }
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++)
+#pragma unroll
+        for (int j = 0; j < 9; j++) {                            // j = kw*3 + c
+            const float v0 = patch[ty + kh][tx * 3 + j];
+            const float v1 = patch[ty + 8 + kh][tx * 3 + j];
+            const float4* wr = reinterpret_cast<const float4*>(ws[kh * 9 + j]);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const float4 w4 = wr[q];
+                a0[4 * q + 0] = fmaf(v0, w4.x, a0[4 * q + 0]); a1[4 * q + 0] = fmaf(v1, w4.x, a1[4 * q + 0]);
+                a0[4 * q + 1] = fmaf(v0, w4.y, a0[4 * q + 1]); a1[4 * q + 1] = fmaf(v1, w4.y, a1[4 * q + 1]);
+                a0[4 * q + 2] = fmaf(v0, w4.z, a0[4 * q + 2]); a1[4 * q + 2] = fmaf(v1, w4.z, a1[4 * q + 2]);
+                a0[4 * q + 3] = fmaf(v0, w4.w, a0[4 * q + 3]); a1[4 * q + 3] = fmaf(v1, w4.w, a1[4 * q + 3]);
+            }
+        }
+    const int Sp = p.S + 2;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int y = y0 + ty + half * 8, x = x0 + tx;
+        if (y >= p.S || x >= p.S) continue;
+        const float* a = half ? a1 : a0;
+        uint4 o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            __half2 h[4];
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                float u0 = a[8 * q + 2 * t] + bs[8 * q + 2 * t], u1 = a[8 * q + 2 * t + 1] + bs[8 * q + 2 * t + 1];
+                u0 = u0 > 0.f ? u0 : 0.1f * u0; u1 = u1 > 0.f ? u1 : 0.1f * u1;          // leaky (custom_layers.py:101 default act)
+                h[t] = __floats2half2_rn(u0, u1);
+            }
+            o[q].x = *reinterpret_cast<uint32_t*>(&h[0]); o[q].y = *reinterpret_cast<uint32_t*>(&h[1]);
+            o[q].z = *reinterpret_cast<uint32_t*>(&h[2]); o[q].w = *reinterpret_cast<uint32_t*>(&h[3]);
+        }
+        uint4* op = reinterpret_cast<uint4*>(p.out + (((long long)n * Sp + y + 1) * Sp + x + 1) * 32);
+#pragma unroll
+        for (int q = 0; q < 4; q++) op[q] = o[q];
+    }
+}
+
 struct SppParams {
     void* buf;            // concat buffer (N, H+2, W+2, ld)
     int ld, N, H, W, C;   // C = channels of x; x lives at channel offset 3*C, outputs at 0, C, 2*C
 };
+
+// fp16 SPP, 8 channels per thread (16 B loads, __hmax2): nested 5 c 9 c 13 windows in one sweep.
+__global__ void spp_half8_kernel(SppParams p) {
+    const int C8 = p.C >> 3;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)p.N * p.H * p.W * C8;
+    if (i >= total) return;
+    const int c8 = (int)(i % C8);
+    long long t = i / C8;
+    const int w = (int)(t % p.W); t /= p.W;
+    const int h = (int)(t % p.H);
+    const int n = (int)(t / p.H);
+    const int Hp = p.H + 2, Wp = p.W + 2;
+    const __half* base = reinterpret_cast<const __half*>(p.buf);
+    const __half2 ninf = __float2half2_rn(-INFINITY);
+    __half2 m5[4], m9[4], m13[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) { m5[k] = ninf; m9[k] = ninf; m13[k] = ninf; }
+    for (int dy = -6; dy <= 6; dy++) {
+        const int hh = h + dy;
+        if (hh < 0 || hh >= p.H) continue;
+        const int ady = dy < 0 ? -dy : dy;
+        for (int dx = -6; dx <= 6; dx++) {
+            const int ww = w + dx;
+            if (ww < 0 || ww >= p.W) continue;
+            const uint4 u = *reinterpret_cast<const uint4*>(base + (((long long)n * Hp + hh + 1) * Wp + ww + 1) * p.ld + 3 * p.C + c8 * 8);
+            const __half2* v = reinterpret_cast<const __half2*>(&u);
+            const int adx = dx < 0 ? -dx : dx;
+            const int d = ady > adx ? ady : adx;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                m13[k] = __hmax2(m13[k], v[k]);
+                if (d <= 4) m9[k] = __hmax2(m9[k], v[k]);
+                if (d <= 2) m5[k] = __hmax2(m5[k], v[k]);
+            }
+        }
+    }
+    __half* ob = reinterpret_cast<__half*>(p.buf) + (((long long)n * Hp + h + 1) * Wp + w + 1) * p.ld + c8 * 8;
+    *reinterpret_cast<uint4*>(ob) = *reinterpret_cast<uint4*>(m13);
+    *reinterpret_cast<uint4*>(ob + p.C) = *reinterpret_cast<uint4*>(m9);
+    *reinterpret_cast<uint4*>(ob + 2 * p.C) = *reinterpret_cast<uint4*>(m5);
+}
+
+// SPP (custom_layers.py:130-134): mp13 | mp9 | mp5 | x, stride 1, 'same' (out-of-range cells ignored).
+// One thread per (n,h,w,c): nested windows 5 c 9 c 13 share one sweep.
 
 template <typename T>
 __global__ void spp_kernel(SppParams p) {

@@ -374,11 +374,22 @@ void launch_spp(y4_engine* e, int batch) {
     long long total = (long long)batch * b.H * b.W * e->spp_C;
     unsigned blocks = (unsigned)((total + 255) / 256);
     if (e->elt == 4) spp_kernel<float><<<blocks, 256, 0, e->stream>>>(p);
+    else if (e->cfg.precision == Y4_PREC_FP16 && e->spp_C % 8 == 0)
+        spp_half8_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, e->stream>>>(p);
     else spp_kernel<__half><<<blocks, 256, 0, e->stream>>>(p);
     e->launches++;
 }
 
+void launch_conv0_direct(y4_engine* e, const ConvOp& c, int batch) {
+    const int S = e->cfg.img_size;
+    Conv0Params p{e->d_img, c.d_w32, c.d_bias, (__half*)e->bufs[c.out.buf].ptr, batch, S, c.cout_pad};
+    dim3 grid((unsigned)((S + 31) / 32), (unsigned)((S + 15) / 16), (unsigned)batch);
+    conv0_direct_kernel<<<grid, 256, 0, e->stream>>>(p);
+    e->launches++;
+}
+
 int run_conv(y4_engine* e, const ConvOp& c, int batch) {
+    if (c.kind == 3) { launch_conv0_direct(e, c, batch); return Y4_OK; }
     if (c.kind == 0) { launch_simt(e, c, batch); return Y4_OK; }
     int rc = tc_launch(c.tc, batch, e->stream);
     if (rc != 0) return fail(e, Y4_ERR_CUDA, "tcgen05 conv launch failed for conv " + std::to_string(c.idx));
@@ -580,10 +591,37 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             if (c.has_res) { const Buf& rb = e->bufs[c.res.buf]; d.res = rb.ptr; d.res_ld = rb.C; d.res_choff = c.res.choff; }
             d.w16 = c.d_w16; d.bias = c.d_bias;
             std::string terr;
+            if (c.raw_in && c.cin == 3 && c.cout == 32 && c.k == 3 && c.act == ACT_LEAKY && c.out.choff == 0 && ob.C == 32) {
+                c.kind = 3;                                    // dedicated direct-conv kernel for conv 0
+                continue;
+            }
             int kind = tc_plan(d, &c.tc, &terr);
             if (kind < 0) return bail(fail(e, Y4_ERR_CUDA, "tcgen05 plan failed for conv " + std::to_string(c.idx) + ": " + terr));
             c.kind = kind;
+            // Plan-time autotune: the N tile / pipeline depth only change scheduling, never the per-element K-sum
+            // order, so every candidate produces bit-identical outputs.  Time each on the (still zero) buffers.
+            const char* at = getenv("Y4_AUTOTUNE");
+            if (kind > 0 && !(at && at[0] == '0')) {
+                const int cand[6][2] = {{64, 99}, {128, 99}, {128, 150}, {256, 99}, {256, 150}, {256, 200}};
+                float best_ms = 1e30f;
+                TcConvPlan best = c.tc;
+                for (auto& cd : cand) {
+                    TcConvPlan trial;
+                    std::string er2;
+                    if (tc_plan(d, &trial, &er2, cd[0], cd[1]) != kind) continue;
+                    if (tc_launch(trial, B, e->stream) != 0) { cudaGetLastError(); continue; }      // warm-up + smem attribute
+                    cudaEventRecord(e->ev0, e->stream);
+                    for (int rep = 0; rep < 3; rep++) tc_launch(trial, B, e->stream);
+                    cudaEventRecord(e->ev1, e->stream);
+                    if (cudaEventSynchronize(e->ev1) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, "autotune launch failed for conv " + std::to_string(c.idx)));
+                    float ms = 0.f;
+                    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+                    if (ms < best_ms) { best_ms = ms; best = trial; }
+                }
+                c.tc = best;
+            }
         }
+        // autotune launches wrote act(bias=0)=0-ish garbage into interiors only; halos were never touched.
     }
     CREATE_TRY(cudaDeviceSynchronize());
     *out = e;
