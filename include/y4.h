@@ -140,6 +140,9 @@ int64_t y4_debug_get_tensor(y4_engine* e, const char* name, int32_t batch, float
  * lets tests compare both kernels on identical inputs.  Synchronises. */
 int  y4_debug_run_conv(y4_engine* e, int32_t idx, int32_t batch, int32_t use_tc);
 
+/* clock64 phase timestamps of one tcgen05 conv launch, 16 int64 per CTA (see y4_engine.cu); tooling only. */
+int  y4_debug_trace_conv(y4_engine* e, int32_t idx, int32_t batch, int64_t* out, int32_t max_ctas);
+
 /* ---- multi-GPU (one process per GPU; images shard, weights replicate) ------------------------------ */
 /* uid: 128-byte ncclUniqueId produced on rank 0 and broadcast by the host launcher. */
 int  y4_comm_unique_id(void* uid128);

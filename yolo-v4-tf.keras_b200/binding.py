@@ -39,7 +39,7 @@ EXPORTS = [
     'y4_run_resident', 'y4_run_forward_resident', 'y4_run_decode_nms_resident', 'y4_upload_heads',
     'y4_fetch_results', 'y4_sync', 'y4_timer_begin', 'y4_timer_end', 'y4_flush_l2', 'y4_launch_count',
     'y4_profile_layers', 'y4_host_alloc', 'y4_host_free', 'y4_num_layers', 'y4_describe_layer', 'y4_num_boxes',
-    'y4_debug_get_tensor', 'y4_debug_run_conv', 'y4_comm_unique_id', 'y4_comm_init', 'y4_allgather_results',
+    'y4_debug_get_tensor', 'y4_debug_run_conv', 'y4_debug_trace_conv', 'y4_comm_unique_id', 'y4_comm_init', 'y4_allgather_results',
 ]
 
 _lib = None
@@ -84,6 +84,7 @@ def load_library():
     lib.y4_debug_get_tensor.argtypes = [vp, C.c_char_p, C.c_int32, vp, C.c_int64]
     lib.y4_debug_get_tensor.restype = C.c_int64
     lib.y4_debug_run_conv.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    lib.y4_debug_trace_conv.argtypes = [vp, C.c_int32, C.c_int32, vp, C.c_int32]
     lib.y4_comm_unique_id.argtypes = [vp]
     lib.y4_comm_init.argtypes = [vp, C.c_int32, C.c_int32, vp]
     lib.y4_allgather_results.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
@@ -266,6 +267,11 @@ class Engine:
 
     def run_conv(self, idx, batch, use_tc):
         self._chk(self._lib.y4_debug_run_conv(self._h, idx, batch, int(use_tc)))
+
+    def trace_conv(self, idx, batch, max_ctas=4096):
+        out = np.zeros((max_ctas, 16), np.int64)
+        self._chk(self._lib.y4_debug_trace_conv(self._h, idx, batch, _ptr(out), max_ctas))
+        return out
 
     # ---- multi-GPU
     def comm_unique_id(self):

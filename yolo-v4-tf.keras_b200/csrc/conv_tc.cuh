@@ -49,6 +49,7 @@ struct TcParams {
     long long M_total;           // batch * Hp * Wp
     // box
     int OH, OW, TH, TW, tiles_w, tiles_per_img;
+    long long* dbg;              // optional per-CTA phase timestamps (y4_debug_trace_conv); nullptr in production
 };
 
 struct TcConvPlan {
@@ -180,6 +181,9 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * BN;
+    long long* dbg = (p.dbg && blockIdx.y == 0 && blockIdx.x < 4096) ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
+#define Y4_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+    if (threadIdx.x == 0) { Y4_STAMP(0); if (dbg) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[15] = sm; long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[14] = gt; } }
 
     // tile coordinates
     long long m0 = 0;
@@ -207,6 +211,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    if (threadIdx.x == 0) Y4_STAMP(1);
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -230,7 +235,9 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, ow0 + (kw >> 1), oh0 + (kh >> 1), img);
                 }
                 tma_load_2d(sa + A_BYTES, &p.tmW, fb, kb * BK, n0);
+                if (kb == 0) Y4_STAMP(2);
             }
+            Y4_STAMP(3);
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
@@ -240,6 +247,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                 const uint32_t ph = (uint32_t)(kb / S) & 1u;
                 mbar_wait(bar_full + 8u * s, ph);
                 tc_fence_after();
+                if (kb == 0) Y4_STAMP(4);
                 const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
                 const uint64_t da = make_smem_desc<SWZ>(sa);
                 const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
@@ -249,6 +257,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                 umma_commit(bar_empty + 8u * s);          // frees this smem stage once the MMAs have read it
             }
             umma_commit(bar_tfull);                       // accumulator complete
+            Y4_STAMP(5);
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
@@ -275,6 +284,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         }
         mbar_wait(bar_tfull, 0);
         tc_fence_after();
+        if (threadIdx.x == 64) Y4_STAMP(6);
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -340,9 +350,12 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             }
         }
     }
+    if (threadIdx.x == 64) Y4_STAMP(7);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+    if (threadIdx.x == 0) Y4_STAMP(8);
+#undef Y4_STAMP
 }
 
 // ------------------------------------------------------------------------------------------------------

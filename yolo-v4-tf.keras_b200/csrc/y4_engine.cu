@@ -872,6 +872,28 @@ int y4_debug_run_conv(y4_engine* e, int32_t idx, int32_t batch, int32_t use_tc) 
     return Y4_OK;
 }
 
+// Phase timestamps of the tcgen05 conv kernel (clock64 per CTA): out[cta*16 + {0 entry,1 setup done,2 first TMA issued,
+// 3 last TMA issued,4 first stage landed,5 last MMA issued,6 accumulator ready,7 epilogue done,8 exit,14 globaltimer,15 smid}]
+int y4_debug_trace_conv(y4_engine* e, int32_t idx, int32_t batch, int64_t* out, int32_t max_ctas) {
+    int rc = ready(e, batch, true); if (rc) return rc;
+    if (idx < 0 || idx >= (int)e->convs.size() || !out || max_ctas < 1) return fail(e, Y4_ERR_ARG, "bad args");
+    const ConvOp& c = e->convs[idx];
+    if (c.kind != 1 && c.kind != 2) return fail(e, Y4_ERR_ARG, "conv has no tcgen05 plan");
+    if (max_ctas > 4096) max_ctas = 4096;
+    long long* d = nullptr;
+    CUDA_TRY(e, cudaMalloc(&d, sizeof(long long) * 16 * 4096));
+    CUDA_TRY(e, cudaMemsetAsync(d, 0, sizeof(long long) * 16 * 4096, e->stream));
+    TcConvPlan pl = c.tc;
+    tc_launch(pl, batch, e->stream);                 // warm
+    pl.p.dbg = d;
+    int lr = tc_launch(pl, batch, e->stream);
+    cudaError_t ce = cudaMemcpyAsync(out, d, sizeof(long long) * 16 * max_ctas, cudaMemcpyDeviceToHost, e->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+    cudaFree(d);
+    if (lr != 0 || ce != cudaSuccess) return fail(e, Y4_ERR_CUDA, "trace launch failed");
+    return Y4_OK;
+}
+
 int64_t y4_debug_get_tensor(y4_engine* e, const char* name, int32_t batch, float* out, int64_t capacity) {
     if (!e || !name) return Y4_ERR_ARG;
     int rc = check_batch(e, batch); if (rc) return rc;
