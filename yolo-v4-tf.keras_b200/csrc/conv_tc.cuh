@@ -149,15 +149,33 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ float act_fast(float x, int act) {
-    if (act == 2) {                                   // mish: x * tanh(softplus(x)) = x * n / (n + 2), n = e^x (e^x + 2)
-        float t = __expf(fminf(x, 20.f));
-        float n = t * (t + 2.f);
-        float m = x * __fdividef(n, n + 2.f);
-        return x > 20.f ? x : m;
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// Branch-free activations (the element loop must stay one basic block so the 32 independent chains interleave:
+// the epilogue runs one warp per scheduler and is issue-latency bound otherwise).
+// mish(x) = x * tanh(softplus(x)) = x * n / (n + 2), n = e^x (e^x + 2); for x > 20 the ratio is exactly 1 in fp32.
+template <int ACT>
+__device__ __forceinline__ float act_tc(float x) {
+    if (ACT == 2) {
+        const float t = ex2_approx(fminf(x, 20.f) * 1.4426950408889634f);
+        const float n = fmaf(t, t, t + t);
+        return x * (n * rcp_approx(n + 2.f));
     }
-    if (act == 1) return x > 0.f ? x : 0.1f * x;
+    if (ACT == 1) return fmaxf(x, 0.1f * x);
     return x;
+}
+
+template <int ACT>
+__device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j));
+        f[j + 0] = act_tc<ACT>(__uint_as_float(v[j + 0]) + b4.x);
+        f[j + 1] = act_tc<ACT>(__uint_as_float(v[j + 1]) + b4.y);
+        f[j + 2] = act_tc<ACT>(__uint_as_float(v[j + 2]) + b4.z);
+        f[j + 3] = act_tc<ACT>(__uint_as_float(v[j + 3]) + b4.w);
+    }
 }
 
 constexpr int kTcThreads = 192;
@@ -294,20 +312,19 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             const int col0 = n0 + c0;
             if (!valid || col0 >= p.cout_store) continue;
             float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                f[j + 0] = act_fast(__uint_as_float(v[j + 0]) + b4.x, p.act);
-                f[j + 1] = act_fast(__uint_as_float(v[j + 1]) + b4.y, p.act);
-                f[j + 2] = act_fast(__uint_as_float(v[j + 2]) + b4.z, p.act);
-                f[j + 3] = act_fast(__uint_as_float(v[j + 3]) + b4.w, p.act);
-            }
-            if (p.res) {
+            uint4 rres[4];
+            if (p.res) {                                   // issue the skip-tile loads before the math that hides them
                 const uint4* rp = reinterpret_cast<const uint4*>(p.res + drow * p.res_ld + p.res_choff + col0);
 #pragma unroll
+                for (int j = 0; j < 4; j++) rres[j] = __ldg(rp + j);
+            }
+            if (p.act == 2) bias_act32<2>(v, p.bias + col0, f);
+            else if (p.act == 1) bias_act32<1>(v, p.bias + col0, f);
+            else bias_act32<0>(v, p.bias + col0, f);
+            if (p.res) {
+#pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    const uint4 u = __ldg(rp + j);
-                    const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&rres[j]);
 #pragma unroll
                     for (int t = 0; t < 4; t++) {
                         const float2 x = __half22float2(h2[t]);
