@@ -14,8 +14,9 @@
 //
 // CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc/free), warps 2..5 epilogue
 // (TMEM -> registers -> bias + activation (+ residual) -> fp16/fp32 global stores, halo rows skipped,
-// optional 2x2 replicated store = fused UpSampling2D).  One 128 x BN output tile per CTA; several CTAs per SM
-// overlap one tile's epilogue with another's main loop.
+// optional 2x2 replicated store = fused UpSampling2D).  PERSISTENT: each CTA loops over 128 x BN output tiles
+// (tile = blockIdx.x, += gridDim.x); the smem ring keeps running across tiles and TMEM holds TWO accumulator
+// stages, so the MMAs of tile i+1 overlap the epilogue of tile i and the per-tile start-up latency is paid once.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -43,6 +44,7 @@ struct TcParams {
     int act, out_f32, upsample;
     int cout_store;              // columns >= cout_store are not written
     int num_kb, kb_per_tap, ksize, stages;
+    int num_tiles, n_tiles, bias_n;   // tiles = m_tiles * n_tiles (n fastest); bias_n floats staged in smem
     int mode;                    // 1 flat, 2 box
     // flat
     int Hp, Wp;                  // padded dims (same for in and out)
@@ -55,7 +57,7 @@ struct TcParams {
 struct TcConvPlan {
     TcParams p;
     int kind = 0;                // 1 flat, 2 box
-    int tile_n = 0, bk = 64, stages = 0;
+    int tile_n = 0, bk = 64, stages = 0, ctas_per_sm = 1;
     size_t smem = 0;
     int in_Hp = 0, in_Wp = 0;
 };
@@ -134,6 +136,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// tcgen05.ld split into issue + wait so the next chunk's TMEM read overlaps the current chunk's math.  The wait
+// names the registers as in/out operands: their first use cannot be scheduled above it.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+          "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+          "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :: "memory");
+}
+
 // K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
 //  [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major: 1) | [32,46) SBO>>4 (8 rows * swizzle bytes)
 //  | [46,48) version = 1 | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B
@@ -170,7 +196,7 @@ template <int ACT>
 __device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + j));
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
         f[j + 0] = act_tc<ACT>(__uint_as_float(v[j + 0]) + b4.x);
         f[j + 1] = act_tc<ACT>(__uint_as_float(v[j + 1]) + b4.y);
         f[j + 2] = act_tc<ACT>(__uint_as_float(v[j + 2]) + b4.z);
@@ -180,13 +206,91 @@ __device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], const float*
 
 constexpr int kTcThreads = 192;
 
+struct TileCoord { long long m0; int img, oh0, ow0, n0; };
+
+template <int BN>
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
+    TileCoord t;
+    const int mt = tile / p.n_tiles;
+    t.n0 = (tile - mt * p.n_tiles) * BN;
+    t.m0 = 0; t.img = 0; t.oh0 = 0; t.ow0 = 0;
+    if (p.mode == 1) {
+        t.m0 = (long long)mt * 128;
+    } else {
+        t.img = mt / p.tiles_per_img;
+        const int r = mt - t.img * p.tiles_per_img;
+        const int th = r / p.tiles_w;
+        t.oh0 = th * p.TH; t.ow0 = (r - th * p.tiles_w) * p.TW;
+    }
+    return t;
+}
+
+// One 32-column chunk of the epilogue for one accumulator row: +bias -> activation -> (+skip) -> store.
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const float* sbias, int col0,
+                                               long long drow, int n, int hp, int wp) {
+    float f[32];
+    uint4 rres[4];
+    if (p.res) {                                           // issue the skip-tile loads before the math that hides them
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + drow * p.res_ld + p.res_choff + col0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) rres[j] = __ldg(rp + j);
+    }
+    if (p.act == 2) bias_act32<2>(v, sbias + col0, f);
+    else if (p.act == 1) bias_act32<1>(v, sbias + col0, f);
+    else bias_act32<0>(v, sbias + col0, f);
+    if (p.res) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const __half2* h2 = reinterpret_cast<const __half2*>(&rres[j]);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float2 x = __half22float2(h2[t]);
+                f[j * 8 + t * 2] += x.x; f[j * 8 + t * 2 + 1] += x.y;
+            }
+        }
+    }
+    if (p.out_f32) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + drow * p.out_ld + p.out_choff + col0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        return;
+    }
+    uint4 o[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        __half2 h0 = __floats2half2_rn(f[8 * j + 0], f[8 * j + 1]);
+        __half2 h1 = __floats2half2_rn(f[8 * j + 2], f[8 * j + 3]);
+        __half2 h2 = __floats2half2_rn(f[8 * j + 4], f[8 * j + 5]);
+        __half2 h3 = __floats2half2_rn(f[8 * j + 6], f[8 * j + 7]);
+        o[j].x = *reinterpret_cast<uint32_t*>(&h0); o[j].y = *reinterpret_cast<uint32_t*>(&h1);
+        o[j].z = *reinterpret_cast<uint32_t*>(&h2); o[j].w = *reinterpret_cast<uint32_t*>(&h3);
+    }
+    __half* ob = reinterpret_cast<__half*>(p.out);
+    if (p.upsample) {
+        const int DHp = 2 * (p.Hp - 2) + 2, DWp = 2 * (p.Wp - 2) + 2;
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                const long long dr = ((long long)n * DHp + 2 * (hp - 1) + 1 + dy) * DWp + 2 * (wp - 1) + 1 + dx;
+                uint4* op = reinterpret_cast<uint4*>(ob + dr * p.out_ld + p.out_choff + col0);
+#pragma unroll
+                for (int j = 0; j < 4; j++) op[j] = o[j];
+            }
+    } else {
+        uint4* op = reinterpret_cast<uint4*>(ob + drow * p.out_ld + p.out_choff + col0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) op[j] = o[j];
+    }
+}
+
 template <int BN, int BK>
 __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int SWZ = BK * 2;
     constexpr int A_BYTES = 128 * BK * 2;
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
+    constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;      // two accumulator stages (power of two: 128/256/512)
     constexpr uint32_t IDESC = make_idesc(128, BN);
 
     extern __shared__ unsigned char tc_smem[];
@@ -194,36 +298,27 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     const uint32_t raw = smem_u32(tc_smem);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const int S = p.stages;
-    const uint32_t bars = base + (uint32_t)S * STAGE_BYTES;          // full[S], empty[S], tmem_full, tmem_slot
-    const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, tmem_slot = bars + 16u * S + 8u;
+    // after the stages: full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), bias[bias_n]
+    const uint32_t bars = base + (uint32_t)S * STAGE_BYTES;
+    const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
+    const uint32_t tmem_slot = bars + 16u * S + 32u;
+    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + (size_t)S * STAGE_BYTES + 16u * S + 48u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.y * BN;
-    long long* dbg = (p.dbg && blockIdx.y == 0 && blockIdx.x < 4096) ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
+    long long* dbg = (p.dbg && blockIdx.x < 4096) ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
 #define Y4_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
     if (threadIdx.x == 0) { Y4_STAMP(0); if (dbg) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[15] = sm; long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[14] = gt; } }
-
-    // tile coordinates
-    long long m0 = 0;
-    int img = 0, oh0 = 0, ow0 = 0;
-    if (p.mode == 1) {
-        m0 = (long long)blockIdx.x * 128;
-    } else {
-        img = blockIdx.x / p.tiles_per_img;
-        int t = blockIdx.x - img * p.tiles_per_img;
-        int th = t / p.tiles_w;
-        oh0 = th * p.TH; ow0 = (t - th * p.tiles_w) * p.TW;
-    }
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmW);
         tma_prefetch_desc(&p.tmA[0]);
         if (p.mode == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
-        mbar_init(bar_tfull, 1);
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 4); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+    if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 128) sbias[i] = p.bias[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -232,142 +327,112 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     if (threadIdx.x == 0) Y4_STAMP(1);
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer: the stage ring runs straight across tile boundaries =====
         if (lane == 0) {
             const uint32_t a_bytes = p.mode == 1 ? (uint32_t)A_BYTES : (uint32_t)(p.TH * p.TW * BK * 2);
-            for (int kb = 0; kb < p.num_kb; kb++) {
-                const int s = kb % S;
-                const uint32_t ph = (uint32_t)(kb / S) & 1u;
-                mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-                const uint32_t fb = bar_full + 8u * s;
-                mbar_expect_tx(fb, a_bytes + (uint32_t)B_BYTES);
-                const int tap = kb / p.kb_per_tap;
-                const int c0 = (kb - tap * p.kb_per_tap) * BK;
-                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
-                if (p.mode == 1) {
-                    int shift = 0;
-                    if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
-                    tma_load_2d(sa, &p.tmA[0], fb, c0, (int)(m0 + shift));
-                } else {
-                    const int kh = tap / 3, kw = tap - kh * 3;
-                    tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, ow0 + (kw >> 1), oh0 + (kh >> 1), img);
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile<BN>(p, tile);
+                for (int kb = 0; kb < p.num_kb; kb++, it++) {
+                    const uint32_t s = it % (uint32_t)S;
+                    const uint32_t ph = (it / (uint32_t)S) & 1u;
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    const uint32_t fb = bar_full + 8u * s;
+                    mbar_expect_tx(fb, a_bytes + (uint32_t)B_BYTES);
+                    const int tap = kb / p.kb_per_tap;
+                    const int c0 = (kb - tap * p.kb_per_tap) * BK;
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    if (p.mode == 1) {
+                        int shift = 0;
+                        if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
+                        tma_load_2d(sa, &p.tmA[0], fb, c0, (int)(tc.m0 + shift));
+                    } else {
+                        const int kh = tap / 3, kw = tap - kh * 3;
+                        tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
+                    }
+                    tma_load_2d(sa + A_BYTES, &p.tmW, fb, kb * BK, tc.n0);
+                    if (it == 0) Y4_STAMP(2);
                 }
-                tma_load_2d(sa + A_BYTES, &p.tmW, fb, kb * BK, n0);
-                if (kb == 0) Y4_STAMP(2);
+                if (tile == (int)blockIdx.x) Y4_STAMP(3);
             }
-            Y4_STAMP(3);
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
+        // ===== MMA issuer: accumulator stage = tile parity =====
         if (lane == 0) {
-            for (int kb = 0; kb < p.num_kb; kb++) {
-                const int s = kb % S;
-                const uint32_t ph = (uint32_t)(kb / S) & 1u;
-                mbar_wait(bar_full + 8u * s, ph);
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
+                const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+                mbar_wait(bar_tempty + 8u * as, aph ^ 1u);          // epilogue has drained this accumulator stage
                 tc_fence_after();
-                if (kb == 0) Y4_STAMP(4);
-                const uint32_t sa = base + (uint32_t)s * STAGE_BYTES;
-                const uint64_t da = make_smem_desc<SWZ>(sa);
-                const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
+                const uint32_t tacc = tmem_base + as * (uint32_t)BN;
+                for (int kb = 0; kb < p.num_kb; kb++, it++) {
+                    const uint32_t s = it % (uint32_t)S;
+                    const uint32_t ph = (it / (uint32_t)S) & 1u;
+                    mbar_wait(bar_full + 8u * s, ph);
+                    tc_fence_after();
+                    if (it == 0) Y4_STAMP(4);
+                    const uint32_t sa = base + s * STAGE_BYTES;
+                    const uint64_t da = make_smem_desc<SWZ>(sa);
+                    const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
 #pragma unroll
-                for (int k = 0; k < BK / 16; k++)
-                    umma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
-                umma_commit(bar_empty + 8u * s);          // frees this smem stage once the MMAs have read it
+                    for (int k = 0; k < BK / 16; k++)
+                        umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+                    umma_commit(bar_empty + 8u * s);        // frees this smem stage once the MMAs have read it
+                }
+                umma_commit(bar_tfull + 8u * as);           // accumulator complete
+                if (ti == 0) Y4_STAMP(5);
             }
-            umma_commit(bar_tfull);                       // accumulator complete
-            Y4_STAMP(5);
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
         const int q = warp & 3;
-        const int r = q * 32 + lane;                      // row of the tile
-        bool valid;
-        long long drow = 0;                               // destination row (non-upsample)
-        int n = 0, hp = 0, wp = 0;
-        if (p.mode == 1) {
-            const long long pr = m0 + r;
-            valid = pr < p.M_total;
-            const unsigned up = (unsigned)(valid ? pr : 0);
-            wp = (int)(up % (unsigned)p.Wp);
-            const unsigned t = up / (unsigned)p.Wp;
-            hp = (int)(t % (unsigned)p.Hp);
-            n = (int)(t / (unsigned)p.Hp);
-            valid = valid && hp >= 1 && hp <= p.Hp - 2 && wp >= 1 && wp <= p.Wp - 2;
-            drow = pr;
-        } else {
-            const int th = r / p.TW, tw = r - th * p.TW;
-            const int oh = oh0 + th, ow = ow0 + tw;
-            valid = (r < p.TH * p.TW) && oh < p.OH && ow < p.OW;
-            drow = ((long long)img * (p.OH + 2) + oh + 1) * (p.OW + 2) + ow + 1;
-        }
-        mbar_wait(bar_tfull, 0);
-        tc_fence_after();
-        if (threadIdx.x == 64) Y4_STAMP(6);
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            __syncwarp();                                  // tcgen05.ld is .sync.aligned: reconverge after per-lane skips
-            tmem_ld32(trow + (uint32_t)c0, v);
-            const int col0 = n0 + c0;
-            if (!valid || col0 >= p.cout_store) continue;
-            float f[32];
-            uint4 rres[4];
-            if (p.res) {                                   // issue the skip-tile loads before the math that hides them
-                const uint4* rp = reinterpret_cast<const uint4*>(p.res + drow * p.res_ld + p.res_choff + col0);
-#pragma unroll
-                for (int j = 0; j < 4; j++) rres[j] = __ldg(rp + j);
-            }
-            if (p.act == 2) bias_act32<2>(v, p.bias + col0, f);
-            else if (p.act == 1) bias_act32<1>(v, p.bias + col0, f);
-            else bias_act32<0>(v, p.bias + col0, f);
-            if (p.res) {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const __half2* h2 = reinterpret_cast<const __half2*>(&rres[j]);
-#pragma unroll
-                    for (int t = 0; t < 4; t++) {
-                        const float2 x = __half22float2(h2[t]);
-                        f[j * 8 + t * 2] += x.x; f[j * 8 + t * 2 + 1] += x.y;
-                    }
-                }
-            }
-            if (p.out_f32) {
-                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + drow * p.out_ld + p.out_choff + col0);
-#pragma unroll
-                for (int j = 0; j < 8; j++) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        const int r = q * 32 + lane;                        // row of the tile
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
+            const TileCoord tc = decode_tile<BN>(p, tile);
+            const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+            bool valid;
+            long long drow = 0;                             // destination row (non-upsample)
+            int n = 0, hp = 0, wp = 0;
+            if (p.mode == 1) {
+                const long long pr = tc.m0 + r;
+                valid = pr < p.M_total;
+                const unsigned up = (unsigned)(valid ? pr : 0);
+                wp = (int)(up % (unsigned)p.Wp);
+                const unsigned t = up / (unsigned)p.Wp;
+                hp = (int)(t % (unsigned)p.Hp);
+                n = (int)(t / (unsigned)p.Hp);
+                valid = valid && hp >= 1 && hp <= p.Hp - 2 && wp >= 1 && wp <= p.Wp - 2;
+                drow = pr;
             } else {
-                uint4 o[4];
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    __half2 h0 = __floats2half2_rn(f[8 * j + 0], f[8 * j + 1]);
-                    __half2 h1 = __floats2half2_rn(f[8 * j + 2], f[8 * j + 3]);
-                    __half2 h2 = __floats2half2_rn(f[8 * j + 4], f[8 * j + 5]);
-                    __half2 h3 = __floats2half2_rn(f[8 * j + 6], f[8 * j + 7]);
-                    o[j].x = *reinterpret_cast<uint32_t*>(&h0); o[j].y = *reinterpret_cast<uint32_t*>(&h1);
-                    o[j].z = *reinterpret_cast<uint32_t*>(&h2); o[j].w = *reinterpret_cast<uint32_t*>(&h3);
-                }
-                __half* ob = reinterpret_cast<__half*>(p.out);
-                if (p.upsample) {
-                    const int DHp = 2 * (p.Hp - 2) + 2, DWp = 2 * (p.Wp - 2) + 2;
-#pragma unroll
-                    for (int dy = 0; dy < 2; dy++)
-#pragma unroll
-                        for (int dx = 0; dx < 2; dx++) {
-                            const long long dr = ((long long)n * DHp + 2 * (hp - 1) + 1 + dy) * DWp + 2 * (wp - 1) + 1 + dx;
-                            uint4* op = reinterpret_cast<uint4*>(ob + dr * p.out_ld + p.out_choff + col0);
-#pragma unroll
-                            for (int j = 0; j < 4; j++) op[j] = o[j];
-                        }
-                } else {
-                    uint4* op = reinterpret_cast<uint4*>(ob + drow * p.out_ld + p.out_choff + col0);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) op[j] = o[j];
-                }
+                const int th = r / p.TW, tw = r - th * p.TW;
+                const int oh = tc.oh0 + th, ow = tc.ow0 + tw;
+                valid = (r < p.TH * p.TW) && oh < p.OH && ow < p.OW;
+                drow = ((long long)tc.img * (p.OH + 2) + oh + 1) * (p.OW + 2) + ow + 1;
             }
+            mbar_wait(bar_tfull + 8u * as, aph);
+            tc_fence_after();
+            if (ti == 0 && threadIdx.x == 64) Y4_STAMP(6);
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN;
+            uint32_t va[32], vb[32];
+            tmem_ld32_issue(tacc, va);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 64) {
+                tmem_ld_wait(va);
+                tmem_ld32_issue(tacc + (uint32_t)(c0 + 32), vb);              // BN is a multiple of 64
+                if (valid && tc.n0 + c0 < p.cout_store) epilogue_chunk(p, va, sbias, tc.n0 + c0, drow, n, hp, wp);
+                __syncwarp();                               // tcgen05.ld / wait are .sync.aligned
+                tmem_ld_wait(vb);
+                if (c0 + 64 < BN) tmem_ld32_issue(tacc + (uint32_t)(c0 + 64), va);
+                if (valid && tc.n0 + c0 + 32 < p.cout_store) epilogue_chunk(p, vb, sbias, tc.n0 + c0 + 32, drow, n, hp, wp);
+                __syncwarp();
+            }
+            // all TMEM reads of this stage have completed (last wait above): hand the stage back to the MMA warp
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(bar_tempty + 8u * as);
+            if (ti == 0 && threadIdx.x == 64) Y4_STAMP(7);
         }
     }
-    if (threadIdx.x == 64) Y4_STAMP(7);
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
@@ -417,16 +482,24 @@ inline cudaError_t launch_inst(const TcConvPlan& pl, dim3 grid, cudaStream_t st)
     return cudaGetLastError();
 }
 
+inline int sm_count() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
 inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
     TcConvPlan pl = pl_in;
-    dim3 grid;
+    long long m_tiles;
     if (pl.kind == 1) {
         pl.p.M_total = (long long)batch * pl.p.Hp * pl.p.Wp;
-        grid.x = (unsigned)((pl.p.M_total + 127) / 128);
+        m_tiles = (pl.p.M_total + 127) / 128;
     } else {
-        grid.x = (unsigned)(batch * pl.p.tiles_per_img);
+        m_tiles = (long long)batch * pl.p.tiles_per_img;
     }
-    grid.y = (unsigned)((pl.p.cout_store + pl.tile_n - 1) / pl.tile_n);
+    pl.p.num_tiles = (int)(m_tiles * pl.p.n_tiles);
+    const int max_ctas = sm_count() * pl.ctas_per_sm;
+    dim3 grid((unsigned)(pl.p.num_tiles < max_ctas ? pl.p.num_tiles : max_ctas));
     cudaError_t e = cudaErrorInvalidValue;
     if (pl.bk == 64) {
         switch (pl.tile_n) {
@@ -514,8 +587,16 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     if (S > 8) S = 8;
     if (S > p.num_kb) S = p.num_kb;
     P.stages = S; p.stages = S;
-    P.smem = 1024 + S * stage_bytes + 16 * S + 16;
+    p.n_tiles = (p.cout_store + bn - 1) / bn;
+    p.bias_n = d.cout_pad;
+    P.smem = 1024 + S * stage_bytes + 16 * S + 48 + 4 * (size_t)p.bias_n;
     if (P.smem > 220 * 1024) { *err = "smem budget exceeded"; return -1; }
+    int cps = (int)((227 * 1024) / (P.smem + 1024));            // +1 KB: per-CTA reserved shared memory
+    const int tmem_cols = 2 * bn;
+    if (cps > 512 / tmem_cols) cps = 512 / tmem_cols;            // two accumulator stages per CTA must all fit in TMEM
+    if (cps > 2) cps = 2;                                        // register file: ~140 regs x 192 threads
+    if (cps < 1) cps = 1;
+    P.ctas_per_sm = cps;
     *pl = P;
     return P.kind;
 }

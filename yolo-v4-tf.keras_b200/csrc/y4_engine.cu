@@ -603,7 +603,8 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             // order, so every candidate produces bit-identical outputs.  Time each on the (still zero) buffers.
             const char* at = getenv("Y4_AUTOTUNE");
             if (kind > 0 && !(at && at[0] == '0')) {
-                const int cand[6][2] = {{64, 99}, {128, 99}, {128, 150}, {256, 99}, {256, 150}, {256, 200}};
+                // {N tile, smem budget KB}: budget sets the ring depth and whether one or two persistent CTAs share an SM
+                const int cand[7][2] = {{64, 99}, {64, 200}, {128, 99}, {128, 150}, {128, 200}, {256, 150}, {256, 200}};
                 float best_ms = 1e30f;
                 TcConvPlan best = c.tc;
                 for (auto& cd : cand) {
