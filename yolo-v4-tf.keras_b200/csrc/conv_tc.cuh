@@ -45,6 +45,8 @@ struct TcParams {
     int cout_store;              // columns >= cout_store are not written
     int num_kb, kb_per_tap, ksize, stages;
     int num_tiles, n_tiles, bias_n;   // tiles = m_tiles * n_tiles (n fastest); bias_n floats staged in smem
+    // mode 3 (3x3 stride 1, A-patch reuse): one (128 + 2*Wp + 2)-row patch per 64-channel block feeds all 9 taps
+    int patch_boxes, patch_bytes, patch_slots, base_off_mode;
     int mode;                    // 1 flat, 2 box
     // flat
     int Hp, Wp;                  // padded dims (same for in and out)
@@ -169,6 +171,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     constexpr uint64_t sbo = (8ull * SWZ_BYTES) >> 4;
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
+// Same, for a matrix that starts at an arbitrary 128 B row of a swizzled buffer (row-shifted views of one patch):
+// bits [49,52) 'matrix base offset' = (start >> 7) & 7 tells the MMA the phase of the 1024 B swizzle pattern.
+template <int SWZ_BYTES>
+__device__ __forceinline__ uint64_t make_smem_desc_bo(uint32_t saddr, int mode) {
+    const uint64_t bo = mode ? (uint64_t)((saddr >> 7) & 7u) : 0ull;
+    return make_smem_desc<SWZ_BYTES>(saddr) | (bo << 49);
+}
 // Instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 [4,6)=1, a/b format F16 = 0, K-major both,
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
@@ -214,7 +223,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
     const int mt = tile / p.n_tiles;
     t.n0 = (tile - mt * p.n_tiles) * BN;
     t.m0 = 0; t.img = 0; t.oh0 = 0; t.ow0 = 0;
-    if (p.mode == 1) {
+    if (p.mode != 2) {
         t.m0 = (long long)mt * 128;
     } else {
         t.img = mt / p.tiles_per_img;
@@ -298,11 +307,15 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     const uint32_t raw = smem_u32(tc_smem);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const int S = p.stages;
-    // after the stages: full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), bias[bias_n]
-    const uint32_t bars = base + (uint32_t)S * STAGE_BYTES;
+    // modes 1,2: S stages of (A | B).   mode 3: patch_slots patches, then S stages of B only.
+    // then: full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), pfull[4], pempty[4], bias[bias_n]
+    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : (uint32_t)S * STAGE_BYTES;
+    const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);      // mode 3: first B stage
+    const uint32_t bars = base + ring_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
     const uint32_t tmem_slot = bars + 16u * S + 32u;
-    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + (size_t)S * STAGE_BYTES + 16u * S + 48u);
+    const uint32_t bar_pfull = bars + 16u * S + 48u, bar_pempty = bars + 16u * S + 80u;
+    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + 16u * S + 112u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* dbg = (p.dbg && blockIdx.x < 4096) ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
@@ -315,6 +328,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         if (p.mode == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
         for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 4); }
+        for (int a = 0; a < 4; a++) { mbar_init(bar_pfull + 8u * a, 1); mbar_init(bar_pempty + 8u * a, 1); }
+        if (p.mode == 3) tma_prefetch_desc(&p.tmA[1]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -331,6 +346,44 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         if (lane == 0) {
             const uint32_t a_bytes = p.mode == 1 ? (uint32_t)A_BYTES : (uint32_t)(p.TH * p.TW * BK * 2);
             uint32_t it = 0;
+            if (p.mode == 3) {
+                // patches run one (tile, channel-block) pair ahead of the B loads; 3 slots make that wait-free
+                const int ncb = p.kb_per_tap;
+                const int my_tiles = ((int)p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+                const int pairs = my_tiles * ncb;
+                const uint32_t PS = (uint32_t)p.patch_slots;
+                uint32_t pit = 0;
+                auto issue_patch = [&](int j) {
+                    const int tile = (int)blockIdx.x + (j / ncb) * (int)gridDim.x;
+                    const int cb = j - (j / ncb) * ncb;
+                    const TileCoord tc = decode_tile<BN>(p, tile);
+                    const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
+                    mbar_wait(bar_pempty + 8u * ps, pph ^ 1u);
+                    const uint32_t fb = bar_pfull + 8u * ps;
+                    mbar_expect_tx(fb, (uint32_t)p.patch_boxes * 32u * (uint32_t)SWZ);
+                    const uint32_t dst = base + ps * (uint32_t)p.patch_bytes;
+                    const int row0 = (int)tc.m0 - p.Wp - 1;
+                    for (int b = 0; b < p.patch_boxes; b++)
+                        tma_load_2d(dst + (uint32_t)b * 32u * (uint32_t)SWZ, &p.tmA[1], fb, cb * BK, row0 + b * 32);
+                    pit++;
+                };
+                if (pairs > 0) issue_patch(0);
+                for (int j = 0; j < pairs; j++) {
+                    if (j + 1 < pairs) issue_patch(j + 1);
+                    const int tile = (int)blockIdx.x + (j / ncb) * (int)gridDim.x;
+                    const int cb = j - (j / ncb) * ncb;
+                    const int n0 = (tile % p.n_tiles) * BN;
+                    for (int tap = 0; tap < 9; tap++, it++) {
+                        const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                        mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                        const uint32_t fb = bar_full + 8u * s;
+                        mbar_expect_tx(fb, (uint32_t)B_BYTES);
+                        tma_load_2d(bring + s * (uint32_t)B_BYTES, &p.tmW, fb, (tap * ncb + cb) * BK, n0);
+                        if (it == 0) Y4_STAMP(2);
+                    }
+                    if (j == 0) Y4_STAMP(3);
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile<BN>(p, tile);
                 for (int kb = 0; kb < p.num_kb; kb++, it++) {
@@ -359,12 +412,36 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer: accumulator stage = tile parity =====
         if (lane == 0) {
-            uint32_t it = 0, ti = 0;
+            uint32_t it = 0, ti = 0, pit = 0;
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
                 const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
                 mbar_wait(bar_tempty + 8u * as, aph ^ 1u);          // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * (uint32_t)BN;
+                if (p.mode == 3) {
+                    const uint32_t PS = (uint32_t)p.patch_slots;
+                    for (int cb = 0; cb < p.kb_per_tap; cb++, pit++) {
+                        const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
+                        mbar_wait(bar_pfull + 8u * ps, pph);
+                        tc_fence_after();
+                        const uint32_t pa = base + ps * (uint32_t)p.patch_bytes;
+                        for (int tap = 0; tap < 9; tap++, it++) {
+                            const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                            mbar_wait(bar_full + 8u * s, ph);
+                            tc_fence_after();
+                            if (it == 0) Y4_STAMP(4);
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            // patch row 0 is output row m0 shifted by -(Wp+1): tap (kh,kw) starts at row kh*Wp + kw
+                            const uint64_t da = make_smem_desc_bo<SWZ>(pa + (uint32_t)(kh * p.Wp + kw) * (uint32_t)SWZ, p.base_off_mode);
+                            const uint64_t db = make_smem_desc<SWZ>(bring + s * (uint32_t)B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++)
+                                umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (cb | tap | k) ? 1u : 0u);
+                            umma_commit(bar_empty + 8u * s);
+                        }
+                        umma_commit(bar_pempty + 8u * ps);      // all 9 taps have read this patch
+                    }
+                } else
                 for (int kb = 0; kb < p.num_kb; kb++, it++) {
                     const uint32_t s = it % (uint32_t)S;
                     const uint32_t ph = (it / (uint32_t)S) & 1u;
@@ -394,7 +471,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             bool valid;
             long long drow = 0;                             // destination row (non-upsample)
             int n = 0, hp = 0, wp = 0;
-            if (p.mode == 1) {
+            if (p.mode != 2) {
                 const long long pr = tc.m0 + r;
                 valid = pr < p.M_total;
                 const unsigned up = (unsigned)(valid ? pr : 0);
@@ -517,7 +594,7 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 }
 
 // returns kernel kind (0 = not eligible -> CUDA-core kernel, 1 = flat GEMM, 2 = strided box), <0 on error
-inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99) {
+inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0) {
     if (d.raw_in) return 0;                                   // conv 0 (cin = 3): CUDA-core kernel
     const int bk = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 0);
     if (!bk) return 0;
@@ -581,15 +658,35 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
                 if (!encode_map(&p.tmA[ph * 2 + pw], b, 4, dims, str, box, swz, err)) return -1;
             }
     }
-    const size_t stage_bytes = (size_t)128 * bk * 2 + (size_t)bn * bk * 2;
-    int S = (int)(((size_t)smem_budget_kb * 1024) / stage_bytes);   // default budget ~100 KB: two CTAs share an SM
+    size_t stage_bytes = (size_t)128 * bk * 2 + (size_t)bn * bk * 2;
+    size_t ring_fixed = 0;
+    if (!patch && getenv("Y4_FORCE_PATCH") && P.kind == 1 && d.k == 3 && bk == 64) { patch = 1; if (smem_budget_kb < 200) smem_budget_kb = 200; }
+    if (patch) {
+        // A-patch reuse (mode 3): 3x3 stride 1, 64-channel blocks; patch = 130 + 2*Wp rows, loaded as 32-row TMA boxes
+        if (P.kind != 1 || d.k != 3 || bk != 64) return 0;
+        const int prow = 130 + 2 * in_Wp;
+        p.patch_boxes = (prow + 31) / 32;
+        p.patch_bytes = ((p.patch_boxes * 32 * swz + 1023) / 1024) * 1024;
+        p.patch_slots = 3;
+        p.mode = 3;
+        p.base_off_mode = 1;
+        if (const char* env = getenv("Y4_BASE_OFFSET")) p.base_off_mode = atoi(env);
+        cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)d.max_batch * in_Hp * in_Wp};
+        cuuint64_t str[1] = {(cuuint64_t)d.in_ld * 2};
+        cuuint32_t box[2] = {(cuuint32_t)bk, 32};
+        if (!encode_map(&p.tmA[1], in_base, 2, dims, str, box, swz, err)) return -1;
+        ring_fixed = (size_t)p.patch_slots * p.patch_bytes;
+        stage_bytes = (size_t)bn * bk * 2;                            // the ring holds B tiles only
+        if ((size_t)smem_budget_kb * 1024 < ring_fixed + 2 * stage_bytes) return 0;
+    }
+    int S = (int)(((size_t)smem_budget_kb * 1024 - ring_fixed) / stage_bytes);   // default budget ~100 KB: two CTAs share an SM
     if (S < 2) S = 2;
     if (S > 8) S = 8;
-    if (S > p.num_kb) S = p.num_kb;
+    if (S > (patch ? 9 * p.kb_per_tap : p.num_kb)) S = patch ? 9 * p.kb_per_tap : p.num_kb;
     P.stages = S; p.stages = S;
     p.n_tiles = (p.cout_store + bn - 1) / bn;
     p.bias_n = d.cout_pad;
-    P.smem = 1024 + S * stage_bytes + 16 * S + 48 + 4 * (size_t)p.bias_n;
+    P.smem = 1024 + ring_fixed + S * stage_bytes + 16 * S + 112 + 4 * (size_t)p.bias_n;
     if (P.smem > 220 * 1024) { *err = "smem budget exceeded"; return -1; }
     int cps = (int)((227 * 1024) / (P.smem + 1024));            // +1 KB: per-CTA reserved shared memory
     const int tmem_cols = 2 * bn;

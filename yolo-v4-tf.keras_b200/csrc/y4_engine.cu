@@ -604,13 +604,16 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             const char* at = getenv("Y4_AUTOTUNE");
             if (kind > 0 && !(at && at[0] == '0')) {
                 // {N tile, smem budget KB}: budget sets the ring depth and whether one or two persistent CTAs share an SM
-                const int cand[7][2] = {{64, 99}, {64, 200}, {128, 99}, {128, 150}, {128, 200}, {256, 150}, {256, 200}};
+                const int cand[10][3] = {{64, 99, 0}, {64, 200, 0}, {128, 99, 0}, {128, 150, 0}, {128, 200, 0}, {256, 150, 0}, {256, 200, 0},
+                                         {64, 205, 1}, {128, 205, 1}, {256, 205, 1}};       // last three: A-patch reuse (3x3 stride 1)
                 float best_ms = 1e30f;
                 TcConvPlan best = c.tc;
+                static const bool allow_patch = !(getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '0');
                 for (auto& cd : cand) {
+                    if (cd[2] && !allow_patch) continue;
                     TcConvPlan trial;
                     std::string er2;
-                    if (tc_plan(d, &trial, &er2, cd[0], cd[1]) != kind) continue;
+                    if (tc_plan(d, &trial, &er2, cd[0], cd[1], cd[2]) != kind) continue;
                     if (tc_launch(trial, B, e->stream) != 0) { cudaGetLastError(); continue; }      // warm-up + smem attribute
                     cudaEventRecord(e->ev0, e->stream);
                     for (int rep = 0; rep < 3; rep++) tc_launch(trial, B, e->stream);
