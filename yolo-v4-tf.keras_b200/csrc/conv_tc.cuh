@@ -669,7 +669,8 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
         p.patch_bytes = ((p.patch_boxes * 32 * swz + 1023) / 1024) * 1024;
         p.patch_slots = 3;
         p.mode = 3;
-        p.base_off_mode = 1;
+        p.base_off_mode = 0;   // measured on B200: the MMA derives the swizzle phase from absolute smem address bits;
+                               // a non-zero 'matrix base offset' double-counts it (tests/test_gpu_tc.py with Y4_BASE_OFFSET=1 fails)
         if (const char* env = getenv("Y4_BASE_OFFSET")) p.base_off_mode = atoi(env);
         cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)d.max_batch * in_Hp * in_Wp};
         cuuint64_t str[1] = {(cuuint64_t)d.in_ld * 2};
