@@ -18,6 +18,7 @@ for idx in map(int, sys.argv[3:]):
     gt = t[:, 14] - t[:, 14].min()
     print(f"\nconv {idx}: {l['cin']}->{l['cout']} k{l['ksize']} s{l['stride']} hw{l['out_hw']} kind{l['kernel_kind']} bn{l['tile_n']}  ctas traced {len(t)}  span {gt.max()/1e3:.1f} us")
     print('  cycles from CTA entry (median / p90): ' + ', '.join(f'{n} {np.median(rel[:, i]):.0f}/{np.percentile(rel[:, i], 90):.0f}' for i, n in enumerate(names)))
+    print(f'  MMA thread: loop {np.median(t[:, 11]):.0f} cyc, waiting on full(data) {np.median(t[:, 9]):.0f}, on patch {np.median(t[:, 13]):.0f}, on tempty(epilogue) {np.median(t[:, 10]):.0f};  producer waiting on empty(slots) {np.median(t[:, 12]):.0f}; tiles/CTA ~{l["flops"] and 0}')
     order = np.argsort(t[:, 14])
     sm = t[:, 15]
     s0 = sm[order[0]]

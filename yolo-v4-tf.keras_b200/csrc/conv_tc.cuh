@@ -92,6 +92,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     while (!mbar_try(bar, parity))
         if (clock64() - t0 > 4000000000ll) __trap();       // ~2 s at 1.9 GHz: orders of magnitude beyond any legal wait
 }
+// debug: wait and add the stall cycles to *acc (used only when tracing)
+__device__ __forceinline__ void mbar_wait_t(uint32_t bar, uint32_t parity, long long* acc) {
+    if (!acc) { mbar_wait(bar, parity); return; }
+    const long long t0 = clock64();
+    mbar_wait(bar, parity);
+    *acc += clock64() - t0;
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -346,6 +353,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         if (lane == 0) {
             const uint32_t a_bytes = p.mode == 1 ? (uint32_t)A_BYTES : (uint32_t)(p.TH * p.TW * BK * 2);
             uint32_t it = 0;
+            long long w_empty = 0;
             if (p.mode == 3) {
                 // patches run one (tile, channel-block) pair ahead of the B loads; 3 slots make that wait-free
                 const int ncb = p.kb_per_tap;
@@ -375,7 +383,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     const int n0 = (tile % p.n_tiles) * BN;
                     for (int tap = 0; tap < 9; tap++, it++) {
                         const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
-                        mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                        mbar_wait_t(bar_empty + 8u * s, ph ^ 1u, dbg ? &w_empty : nullptr);
                         const uint32_t fb = bar_full + 8u * s;
                         mbar_expect_tx(fb, (uint32_t)B_BYTES);
                         tma_load_2d(bring + s * (uint32_t)B_BYTES, &p.tmW, fb, (tap * ncb + cb) * BK, n0);
@@ -389,7 +397,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                 for (int kb = 0; kb < p.num_kb; kb++, it++) {
                     const uint32_t s = it % (uint32_t)S;
                     const uint32_t ph = (it / (uint32_t)S) & 1u;
-                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    mbar_wait_t(bar_empty + 8u * s, ph ^ 1u, dbg ? &w_empty : nullptr);
                     const uint32_t fb = bar_full + 8u * s;
                     mbar_expect_tx(fb, a_bytes + (uint32_t)B_BYTES);
                     const int tap = kb / p.kb_per_tap;
@@ -408,26 +416,29 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                 }
                 if (tile == (int)blockIdx.x) Y4_STAMP(3);
             }
+            if (dbg) dbg[12] = w_empty;
         }
     } else if (warp == 1) {
         // ===== MMA issuer: accumulator stage = tile parity =====
         if (lane == 0) {
             uint32_t it = 0, ti = 0, pit = 0;
+            long long w_full = 0, w_tempty = 0, w_pfull = 0;
+            const long long t_mma0 = clock64();
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
                 const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
-                mbar_wait(bar_tempty + 8u * as, aph ^ 1u);          // epilogue has drained this accumulator stage
+                mbar_wait_t(bar_tempty + 8u * as, aph ^ 1u, dbg ? &w_tempty : nullptr);   // epilogue has drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * (uint32_t)BN;
                 if (p.mode == 3) {
                     const uint32_t PS = (uint32_t)p.patch_slots;
                     for (int cb = 0; cb < p.kb_per_tap; cb++, pit++) {
                         const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
-                        mbar_wait(bar_pfull + 8u * ps, pph);
+                        mbar_wait_t(bar_pfull + 8u * ps, pph, dbg ? &w_pfull : nullptr);
                         tc_fence_after();
                         const uint32_t pa = base + ps * (uint32_t)p.patch_bytes;
                         for (int tap = 0; tap < 9; tap++, it++) {
                             const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
-                            mbar_wait(bar_full + 8u * s, ph);
+                            mbar_wait_t(bar_full + 8u * s, ph, dbg ? &w_full : nullptr);
                             tc_fence_after();
                             if (it == 0) Y4_STAMP(4);
                             const int kh = tap / 3, kw = tap - kh * 3;
@@ -445,7 +456,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                 for (int kb = 0; kb < p.num_kb; kb++, it++) {
                     const uint32_t s = it % (uint32_t)S;
                     const uint32_t ph = (it / (uint32_t)S) & 1u;
-                    mbar_wait(bar_full + 8u * s, ph);
+                    mbar_wait_t(bar_full + 8u * s, ph, dbg ? &w_full : nullptr);
                     tc_fence_after();
                     if (it == 0) Y4_STAMP(4);
                     const uint32_t sa = base + s * STAGE_BYTES;
@@ -459,6 +470,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                 umma_commit(bar_tfull + 8u * as);           // accumulator complete
                 if (ti == 0) Y4_STAMP(5);
             }
+            if (dbg) { dbg[9] = w_full; dbg[10] = w_tempty; dbg[11] = clock64() - t_mma0; dbg[13] = w_pfull; }
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
