@@ -82,21 +82,47 @@ def test_fp32_predict_end_to_end(weights, size):
     eng.close()
 
 
+def _match_detections(ref, got, iou_thr=0.9, score_tol=0.05):
+    """fraction of reference detections (image 0) matched by a same-class engine detection with IoU > iou_thr."""
+    rb, rs, rc, rv = ref[0][0], ref[1][0], ref[2][0], int(ref[3][0])
+    gb, gs, gc, gv = got[0][0], got[1][0], got[2][0], int(got[3][0])
+    hit = 0
+    for i in range(rv):
+        best = 0.0
+        for j in range(gv):
+            if gc[j] != rc[i] or abs(gs[j] - rs[i]) > score_tol:
+                continue
+            x1, y1 = max(rb[i, 0], gb[j, 0]), max(rb[i, 1], gb[j, 1])
+            x2, y2 = min(rb[i, 2], gb[j, 2]), min(rb[i, 3], gb[j, 3])
+            inter = max(x2 - x1, 0) * max(y2 - y1, 0)
+            ua = (rb[i, 2] - rb[i, 0]) * (rb[i, 3] - rb[i, 1]) + (gb[j, 2] - gb[j, 0]) * (gb[j, 3] - gb[j, 1]) - inter
+            best = max(best, inter / ua if ua > 0 else 0.0)
+        hit += best > iou_thr
+    return hit / max(rv, 1)
+
+
 def test_fp16_heads_close(weights):
-    """fp16 storage/operands (fp32 accumulate): heads within a few 1e-2 of the fp32 oracle, measured and reported."""
+    """fp16 tensor-core mode (fp16 operands/activations, fp32 accumulate): it cannot meet the 1e-4 fp32 tolerance -
+    no fp16 pipeline can - so its deviation from the fp32 oracle is MEASURED and bounded: relative RMS of the raw
+    heads < 2e-2, and >= 90 % of the oracle's detections re-found (same class, IoU > 0.9, |score diff| < 0.05)."""
     import y4b200
     import y4_oracle as O
     W, blob = weights
-    size, batch = 160, 2
+    size, batch = 416, 1
     imgs = O.synth_images(0, 0, batch, size)
     heads = O.forward(imgs, W)
+    ref = O.decode_nms(heads, size)
     for prec, tag in ((y4b200.PREC_FP16_SIMT, 'fp16_simt'), (y4b200.PREC_FP16, 'fp16_tc')):
         eng = y4b200.Engine(img_size=size, max_batch=batch, precision=prec)
         eng.load_darknet_bytes(blob)
         got = eng.forward_heads(imgs)
-        errs = [_rel(a, b) for a, b in zip(got, heads)]
-        report(tag + '_heads', errs=errs, kinds=[l['kernel_kind'] for l in eng.layers()])
-        assert max(errs) < 6e-2, errs
+        rms = [float(np.sqrt(np.mean((a - b) ** 2)) / np.sqrt(np.mean(b ** 2))) for a, b in zip(got, heads)]
+        mx = [_rel(a, b) for a, b in zip(got, heads)]
+        det = eng.predict(imgs)
+        agree = _match_detections(ref, det)
+        report(tag + '_heads', rel_rms=rms, rel_max=mx, detections_refound=agree, valid=int(det[3][0]), ref_valid=int(ref[3][0]))
+        assert max(rms) < 2e-2, rms
+        assert agree >= 0.9, agree
         eng.close()
 
 

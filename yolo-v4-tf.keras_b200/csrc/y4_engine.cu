@@ -27,6 +27,7 @@
 #include "kernels_simt.cuh"
 #include "decode_nms.cuh"
 #include "conv_tc.cuh"
+#include "conv0_tc.cuh"
 
 using namespace y4;
 
@@ -61,6 +62,7 @@ struct ConvOp {
     float* d_w32 = nullptr;    // [K][cout_pad]
     float* d_bias = nullptr;   // [cout_pad]
     __half* d_w16 = nullptr;   // [cout_pad][K]  (tcgen05 path)
+    __half* d_w16k32 = nullptr; // conv 0 only: [32][32], K zero-padded 27 -> 32 (conv0_tc.cuh)
     int kind = 0;              // 0 simt, 1 tc flat, 2 tc box
     TcConvPlan tc;             // tensor maps + tile config (conv_tc.cuh)
     std::string out_name;
@@ -389,8 +391,18 @@ void launch_conv0_direct(y4_engine* e, const ConvOp& c, int batch) {
     e->launches++;
 }
 
+void launch_conv0_tc(y4_engine* e, const ConvOp& c, int batch) {
+    const int S = e->cfg.img_size;
+    Conv0TcParams p{e->d_img, c.d_w16k32, c.d_bias, (__half*)e->bufs[c.out.buf].ptr, batch, S, (S + 127) / 128, 0};
+    p.num_tiles = batch * S * p.tiles_per_row;
+    const int max_ctas = sm_count() * 12;
+    conv0_tc_kernel<<<p.num_tiles < max_ctas ? p.num_tiles : max_ctas, kC0Threads, 0, e->stream>>>(p);
+    e->launches++;
+}
+
 int run_conv(y4_engine* e, const ConvOp& c, int batch) {
     if (c.kind == 3) { launch_conv0_direct(e, c, batch); return Y4_OK; }
+    if (c.kind == 4) { launch_conv0_tc(e, c, batch); return Y4_OK; }
     if (c.kind == 0) { launch_simt(e, c, batch); return Y4_OK; }
     int rc = tc_launch(c.tc, batch, e->stream);
     if (rc != 0) return fail(e, Y4_ERR_CUDA, "tcgen05 conv launch failed for conv " + std::to_string(c.idx));
@@ -501,6 +513,12 @@ int upload_weights(y4_engine* e, const unsigned char* data, size_t nbytes) {
         off += 4ull * c.cout * c.cin * kk;
         CUDA_TRY(e, cudaMemcpy(c.d_w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(e, cudaMemcpy(c.d_w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+        if (c.d_w16k32) {
+            std::vector<__half> wk(32 * 32, __float2half(0.f));
+            for (int o = 0; o < c.cout && o < 32; o++)
+                for (int k = 0; k < c.K && k < 32; k++) wk[o * 32 + k] = w16[(size_t)o * c.K + k];
+            CUDA_TRY(e, cudaMemcpy(c.d_w16k32, wk.data(), wk.size() * 2, cudaMemcpyHostToDevice));
+        }
         CUDA_TRY(e, cudaMemcpy(c.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
     }
     e->weights_loaded = true;
@@ -562,6 +580,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     for (auto& c : e->convs) {
         CREATE_TRY(cudaMalloc(&c.d_w32, sizeof(float) * c.K * c.cout_pad));
         CREATE_TRY(cudaMalloc(&c.d_w16, sizeof(__half) * c.K * c.cout_pad));
+        if (c.raw_in && c.K == 27 && c.cout == 32) { CREATE_TRY(cudaMalloc(&c.d_w16k32, sizeof(__half) * 32 * 32)); CREATE_TRY(cudaMemset(c.d_w16k32, 0, sizeof(__half) * 32 * 32)); }
         CREATE_TRY(cudaMalloc(&c.d_bias, sizeof(float) * c.cout_pad));
     }
     for (int i = 0; i < 3; i++)
@@ -593,7 +612,9 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             d.w16 = c.d_w16; d.bias = c.d_bias;
             std::string terr;
             if (c.raw_in && c.cin == 3 && c.cout == 32 && c.k == 3 && c.act == ACT_LEAKY && c.out.choff == 0 && ob.C == 32) {
-                c.kind = 3;                                    // dedicated direct-conv kernel for conv 0
+                // conv 0: tensor-core kernel (in-register im2col, kind 4) unless Y4_C0=direct (CUDA-core direct conv, kind 3)
+                const char* c0 = getenv("Y4_C0");
+                c.kind = (c0 && c0[0] == 'd') || !c.d_w16k32 ? 3 : 4;
                 continue;
             }
             int kind = tc_plan(d, &c.tc, &terr);
@@ -640,7 +661,7 @@ void y4_destroy(y4_engine* e) {
     for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.first);
     if (e->comm) nccl().CommDestroy(e->comm);
     for (auto& b : e->bufs) cudaFree(b.ptr);
-    for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_bias); }
+    for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_w16k32); cudaFree(c.d_bias); }
     cudaFree(e->d_img);
     for (int i = 0; i < 3; i++) cudaFree(e->d_user_heads[i]);
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
