@@ -629,7 +629,10 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                                          {64, 205, 1}, {128, 205, 1}, {256, 205, 1}};       // last three: A-patch reuse (3x3 stride 1)
                 float best_ms = 1e30f;
                 TcConvPlan best = c.tc;
-                static const bool allow_patch = !(getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '0');
+                // A-patch reuse sums K in a different order (channel-block outer, tap inner), so unlike the tile
+                // candidates it is NOT bit-identical to mode 1; it is opt-in (Y4_PATCH=1) to keep results independent
+                // of what the autotuner picks on a given GPU / batch size (multi-GPU gathers are compared bitwise).
+                static const bool allow_patch = getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '1';
                 for (auto& cd : cand) {
                     if (cd[2] && !allow_patch) continue;
                     TcConvPlan trial;
