@@ -43,7 +43,7 @@ struct TcParams {
     int out_ld, out_choff, res_ld, res_choff;
     int act, out_f32, upsample;
     int cout_store;              // columns >= cout_store are not written
-    int num_kb, kb_per_tap, ksize, stages;
+    int num_kb, kb_per_tap, ksize, stages, group;
     int num_tiles, n_tiles, bias_n;   // tiles = m_tiles * n_tiles (n fastest); bias_n floats staged in smem
     // mode 3 (3x3 stride 1, A-patch reuse): one (128 + 2*Wp + 2)-row patch per 64-channel block feeds all 9 taps
     int patch_boxes, patch_bytes, patch_slots, base_off_mode;
@@ -314,9 +314,10 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     const uint32_t raw = smem_u32(tc_smem);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const int S = p.stages;
-    // modes 1,2: S stages of (A | B).   mode 3: patch_slots patches, then S stages of B only.
+    const int G = p.group;                                  // k-blocks per stage (modes 1,2)
+    // modes 1,2: S stages of G x (A | B).   mode 3: patch_slots patches, then S stages of B only.
     // then: full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), pfull[4], pempty[4], bias[bias_n]
-    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : (uint32_t)S * STAGE_BYTES;
+    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : (uint32_t)(S * G) * STAGE_BYTES;
     const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);      // mode 3: first B stage
     const uint32_t bars = base + ring_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
@@ -394,24 +395,30 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             } else
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile<BN>(p, tile);
-                for (int kb = 0; kb < p.num_kb; kb++, it++) {
+                // a stage holds `group` k-blocks behind ONE barrier: the per-barrier latency of the single issuing
+                // threads (try_wait ~90 cycles, fence, commit) is paid once per group, not once per 64-deep k-block
+                for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
                     const uint32_t s = it % (uint32_t)S;
                     const uint32_t ph = (it / (uint32_t)S) & 1u;
                     mbar_wait_t(bar_empty + 8u * s, ph ^ 1u, dbg ? &w_empty : nullptr);
                     const uint32_t fb = bar_full + 8u * s;
-                    mbar_expect_tx(fb, a_bytes + (uint32_t)B_BYTES);
-                    const int tap = kb / p.kb_per_tap;
-                    const int c0 = (kb - tap * p.kb_per_tap) * BK;
-                    const uint32_t sa = base + s * STAGE_BYTES;
-                    if (p.mode == 1) {
-                        int shift = 0;
-                        if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
-                        tma_load_2d(sa, &p.tmA[0], fb, c0, (int)(tc.m0 + shift));
-                    } else {
-                        const int kh = tap / 3, kw = tap - kh * 3;
-                        tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
+                    const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
+                    mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES));
+                    for (int kk = 0; kk < gcount; kk++) {
+                        const int kb = kb0 + kk;
+                        const int tap = kb / p.kb_per_tap;
+                        const int c0 = (kb - tap * p.kb_per_tap) * BK;
+                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * STAGE_BYTES;
+                        if (p.mode == 1) {
+                            int shift = 0;
+                            if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
+                            tma_load_2d(sa, &p.tmA[0], fb, c0, (int)(tc.m0 + shift));
+                        } else {
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
+                        }
+                        tma_load_2d(sa + A_BYTES, &p.tmW, fb, kb * BK, tc.n0);
                     }
-                    tma_load_2d(sa + A_BYTES, &p.tmW, fb, kb * BK, tc.n0);
                     if (it == 0) Y4_STAMP(2);
                 }
                 if (tile == (int)blockIdx.x) Y4_STAMP(3);
@@ -453,18 +460,21 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                         umma_commit(bar_pempty + 8u * ps);      // all 9 taps have read this patch
                     }
                 } else
-                for (int kb = 0; kb < p.num_kb; kb++, it++) {
+                for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
                     const uint32_t s = it % (uint32_t)S;
                     const uint32_t ph = (it / (uint32_t)S) & 1u;
                     mbar_wait_t(bar_full + 8u * s, ph, dbg ? &w_full : nullptr);
                     tc_fence_after();
                     if (it == 0) Y4_STAMP(4);
-                    const uint32_t sa = base + s * STAGE_BYTES;
-                    const uint64_t da = make_smem_desc<SWZ>(sa);
-                    const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
+                    const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
+                    for (int kk = 0; kk < gcount; kk++) {
+                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * STAGE_BYTES;
+                        const uint64_t da = make_smem_desc<SWZ>(sa);
+                        const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++)
-                        umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; k++)
+                            umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
+                    }
                     umma_commit(bar_empty + 8u * s);        // frees this smem stage once the MMAs have read it
                 }
                 umma_commit(bar_tfull + 8u * as);           // accumulator complete
@@ -606,7 +616,7 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 }
 
 // returns kernel kind (0 = not eligible -> CUDA-core kernel, 1 = flat GEMM, 2 = strided box), <0 on error
-inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0) {
+inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0, int group = 1) {
     if (d.raw_in) return 0;                                   // conv 0 (cin = 3): CUDA-core kernel
     const int bk = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 0);
     if (!bk) return 0;
@@ -692,10 +702,17 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
         stage_bytes = (size_t)bn * bk * 2;                            // the ring holds B tiles only
         if ((size_t)smem_budget_kb * 1024 < ring_fixed + 2 * stage_bytes) return 0;
     }
+    if (patch || group < 1) group = 1;
+    if (group > p.num_kb) group = p.num_kb;
+    p.group = group;
+    stage_bytes *= (size_t)group;
     int S = (int)(((size_t)smem_budget_kb * 1024 - ring_fixed) / stage_bytes);   // default budget ~100 KB: two CTAs share an SM
-    if (S < 2) S = 2;
+    if (S < 2) { if (group > 1) return 0; S = 2; }
     if (S > 8) S = 8;
-    if (S > (patch ? 9 * p.kb_per_tap : p.num_kb)) S = patch ? 9 * p.kb_per_tap : p.num_kb;
+    const int max_useful = patch ? 9 * p.kb_per_tap : (p.num_kb + group - 1) / group;
+    if (S > max_useful && group == 1) S = max_useful;
+    if (S > max_useful + 1) S = max_useful + 1;
+    if (S < 2) S = 2;
     P.stages = S; p.stages = S;
     p.n_tiles = (p.cout_store + bn - 1) / bn;
     p.bias_n = d.cout_pad;

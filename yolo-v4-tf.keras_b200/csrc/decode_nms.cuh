@@ -67,6 +67,8 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(DecodeParams p) {
     float obj[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) obj[a] = sigmoid_rn(ptr[a * p.C + 4]);
+    // score = obj * cls <= obj (cls <= 1, round-to-nearest product): nothing in this cell can pass -> warp-uniform exit
+    if (!(obj[0] > p.score_thr || obj[1] > p.score_thr || obj[2] > p.score_thr)) return;
     unsigned anymask = 0;
     const int total = 3 * p.C;
     const int iters = (total + 31) >> 5;
@@ -194,20 +196,30 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
             hi = a;
         }
         int nsel = 0;
-        for (int i = lo; i < hi && nsel < p.max_boxes; i++) {
-            const unsigned long long key = keys[i];
-            const int n = (int)(key & 0xFFFFFFull);
-            const float4 b = boxes[n];
-            bool sup = false;
-            for (int j = lane; j < nsel; j += 32) sup |= iou_tf(b, mybox[j]) > p.iou_thr;   // strict >
-            if (!__any_sync(0xffffffffu, sup)) {
-                if (lane == 0) {
-                    mybox[nsel] = b;
-                    const float score = __uint_as_float(~(unsigned)((key >> 24) & 0xFFFFFFFFull));
-                    sel[atomicAdd(&selcount, 1)] = merge_key(c, score, n);
+        // candidates are visited in score order; their boxes are fetched 32 at a time (one global round trip per
+        // batch instead of one per candidate) and broadcast lane by lane
+        for (int base = lo; base < hi && nsel < p.max_boxes; base += 32) {
+            const int mine = base + lane;
+            unsigned long long mykey = 0ull;
+            float4 mybx = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mine < hi) { mykey = keys[mine]; mybx = boxes[(int)(mykey & 0xFFFFFFull)]; }
+            const int cnt32 = hi - base < 32 ? hi - base : 32;
+            for (int j = 0; j < cnt32 && nsel < p.max_boxes; j++) {
+                float4 b;
+                b.x = __shfl_sync(0xffffffffu, mybx.x, j); b.y = __shfl_sync(0xffffffffu, mybx.y, j);
+                b.z = __shfl_sync(0xffffffffu, mybx.z, j); b.w = __shfl_sync(0xffffffffu, mybx.w, j);
+                const unsigned long long key = __shfl_sync(0xffffffffu, mykey, j);
+                bool sup = false;
+                for (int t = lane; t < nsel; t += 32) sup |= iou_tf(b, mybox[t]) > p.iou_thr;   // strict >
+                if (!__any_sync(0xffffffffu, sup)) {
+                    if (lane == 0) {
+                        mybox[nsel] = b;
+                        const float score = __uint_as_float(~(unsigned)((key >> 24) & 0xFFFFFFFFull));
+                        sel[atomicAdd(&selcount, 1)] = merge_key(c, score, (int)(key & 0xFFFFFFull));
+                    }
+                    nsel++;
+                    __syncwarp();
                 }
-                nsel++;
-                __syncwarp();
             }
         }
     }

@@ -625,8 +625,12 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             const char* at = getenv("Y4_AUTOTUNE");
             if (kind > 0 && !(at && at[0] == '0')) {
                 // {N tile, smem budget KB}: budget sets the ring depth and whether one or two persistent CTAs share an SM
-                const int cand[10][3] = {{64, 99, 0}, {64, 200, 0}, {128, 99, 0}, {128, 150, 0}, {128, 200, 0}, {256, 150, 0}, {256, 200, 0},
-                                         {64, 205, 1}, {128, 205, 1}, {256, 205, 1}};       // last three: A-patch reuse (3x3 stride 1)
+                // {N tile, smem budget KB, A-patch reuse, k-blocks per stage}
+                const int cand[][4] = {{64, 99, 0, 1}, {64, 200, 0, 1}, {128, 99, 0, 1}, {128, 150, 0, 1}, {128, 200, 0, 1},
+                                       {256, 150, 0, 1}, {256, 200, 0, 1},
+                                       {64, 99, 0, 2}, {64, 205, 0, 3}, {64, 205, 0, 99}, {128, 205, 0, 2}, {128, 205, 0, 3},
+                                       {128, 205, 0, 99}, {256, 205, 0, 2},
+                                       {64, 205, 1, 1}, {128, 205, 1, 1}, {256, 205, 1, 1}};     // last three: A-patch reuse
                 float best_ms = 1e30f;
                 TcConvPlan best = c.tc;
                 // A-patch reuse sums K in a different order (channel-block outer, tap inner), so unlike the tile
@@ -637,7 +641,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                     if (cd[2] && !allow_patch) continue;
                     TcConvPlan trial;
                     std::string er2;
-                    if (tc_plan(d, &trial, &er2, cd[0], cd[1], cd[2]) != kind) continue;
+                    if (tc_plan(d, &trial, &er2, cd[0], cd[1], cd[2], cd[3]) != kind) continue;
                     if (tc_launch(trial, B, e->stream) != 0) { cudaGetLastError(); continue; }      // warm-up + smem attribute
                     cudaEventRecord(e->ev0, e->stream);
                     for (int rep = 0; rep < 3; rep++) tc_launch(trial, B, e->stream);
