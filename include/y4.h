@@ -35,6 +35,8 @@ extern "C" {
 #define Y4_PREC_FP32        0      /* fp32 activations, CUDA-core FFMA implicit GEMM (parity mode)          */
 #define Y4_PREC_FP16        1      /* fp16 activations/weights, fp32 accumulate in TMEM, tcgen05 + TMA       */
 #define Y4_PREC_FP16_SIMT   2      /* fp16 storage, CUDA-core kernels (debug reference for the tcgen05 path) */
+#define Y4_PREC_FP16X3      3      /* tensor-core parity mode: activations and weights as fp16 hi+lo pairs, three
+                                      tcgen05 MMAs per k-step (a_hi*b_hi + a_hi*b_lo + a_lo*b_hi), fp32 accumulate  */
 
 typedef struct y4_engine y4_engine;
 

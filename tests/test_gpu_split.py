@@ -1,0 +1,61 @@
+"""Y4_PREC_FP16X3 — the tensor-core parity mode: fp16 hi+lo operands, three tcgen05 MMAs per k-step, fp32 accumulate.
+Held to the same bar as the fp32 CUDA-core mode (tests/test_gpu_forward.py): as close to the float64 evaluation as
+the fp32 oracle itself layer by layer, bit-exact detections and north-star 1e-4 on boxes/scores end to end."""
+import numpy as np
+import pytest
+
+from conftest import report
+from test_gpu_forward import _rel, _stable_case
+
+pytestmark = pytest.mark.gpu
+
+
+def test_split_layer_by_layer(weights):
+    import y4b200
+    import y4_oracle as O
+    W, blob = weights
+    size, batch = 160, 2
+    imgs = O.synth_images(0, 0, batch, size)
+    k32, k64 = {}, {}
+    heads = O.forward(imgs, W, keep=k32)
+    O.forward(imgs, W, np.float64, keep=k64)
+    eng = y4b200.Engine(img_size=size, max_batch=batch, precision=y4b200.PREC_FP16X3)
+    eng.load_darknet_bytes(blob)
+    got_heads = eng.forward_heads(imgs)
+    kinds = [l['kernel_kind'] for l in eng.layers()]
+    assert sum(k in (1, 2) for k in kinds) >= 100, kinds          # it IS the tcgen05 path
+    rows = []
+    for name, ref in k64.items():
+        try:
+            got = eng.get_tensor(name, batch).reshape(ref.shape)
+        except y4b200.Y4Error:
+            continue
+        rows.append((name, _rel(got, ref), _rel(k32[name], ref)))
+    worst = sorted(rows, key=lambda r: -r[1])[:6]
+    report('split_layerwise', n=len(rows), worst=worst, heads_vs_fp32=[_rel(a, b) for a, b in zip(got_heads, heads)])
+    assert len(rows) >= 90
+    for name, e_eng, e_ora in rows:
+        assert e_eng <= 6 * e_ora + 5e-6, (name, e_eng, e_ora)
+    for a, b in zip(got_heads, heads):
+        assert _rel(a, b) < 3e-4
+    eng.close()
+
+
+@pytest.mark.parametrize('size', [256, 416])
+def test_split_predict_end_to_end(weights, size):
+    import y4b200
+    W, blob = weights
+    imgs, ref, noise, first = _stable_case(W, size)
+    tol = max(1e-4, 3 * noise)
+    eng = y4b200.Engine(img_size=size, max_batch=1, precision=y4b200.PREC_FP16X3)
+    eng.load_darknet_bytes(blob)
+    got = eng.predict(imgs, with_indices=True)
+    report(f'split_predict_{size}', first=first, oracle_noise=noise, tol=tol, valid=ref[3].tolist(), got_valid=got[3].tolist(),
+           box_err=float(np.abs(got[0] - ref[0]).max()), score_err=float(np.abs(got[1] - ref[1]).max()),
+           idx_equal=bool(np.array_equal(got[4], ref[4])))
+    assert np.array_equal(got[3], ref[3])
+    assert np.array_equal(got[4], ref[4])
+    assert np.array_equal(got[2], ref[2])
+    assert np.abs(got[0] - ref[0]).max() <= tol
+    assert np.abs(got[1] - ref[1]).max() <= tol
+    eng.close()

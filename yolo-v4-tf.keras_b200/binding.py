@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 
-PREC_FP32, PREC_FP16, PREC_FP16_SIMT = 0, 1, 2
+PREC_FP32, PREC_FP16, PREC_FP16_SIMT, PREC_FP16X3 = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 

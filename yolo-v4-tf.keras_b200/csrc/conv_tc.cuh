@@ -32,14 +32,22 @@ struct TcConvDesc {
     void* out; int out_ld, out_choff, out_f32, upsample;
     const void* res; int res_ld, res_choff;
     const __half* w16; const float* bias;
+    // split precision (Y4_PREC_FP16X3): low-order fp16 planes of activations / weights, per-cout power-of-two weight scale
+    int split; const void* in_lo; void* out_lo; const void* res_lo; const __half* w16_lo; const float* wscale;
 };
 
 struct TcParams {
     CUtensorMap tmA[4];
     CUtensorMap tmW;
+    CUtensorMap tmA_lo[4];       // split precision: low-order planes
+    CUtensorMap tmW_lo;
     const float* bias;
+    const float* wscale;         // per-cout 1/scale of the (power-of-two scaled) split weights, nullptr -> 1
     void* out;
+    void* out_lo;
     const __half* res;
+    const __half* res_lo;
+    int split;
     int out_ld, out_choff, res_ld, res_choff;
     int act, out_f32, upsample;
     int cout_store;              // columns >= cout_store are not written
@@ -209,14 +217,15 @@ __device__ __forceinline__ float act_tc(float x) {
 }
 
 template <int ACT>
-__device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
+__device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], const float* __restrict__ bias, const float* __restrict__ scale, float (&f)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
-        f[j + 0] = act_tc<ACT>(__uint_as_float(v[j + 0]) + b4.x);
-        f[j + 1] = act_tc<ACT>(__uint_as_float(v[j + 1]) + b4.y);
-        f[j + 2] = act_tc<ACT>(__uint_as_float(v[j + 2]) + b4.z);
-        f[j + 3] = act_tc<ACT>(__uint_as_float(v[j + 3]) + b4.w);
+        const float4 s4 = *reinterpret_cast<const float4*>(scale + j);       // 1.0 unless split-precision weights were scaled
+        f[j + 0] = act_tc<ACT>(fmaf(__uint_as_float(v[j + 0]), s4.x, b4.x));
+        f[j + 1] = act_tc<ACT>(fmaf(__uint_as_float(v[j + 1]), s4.y, b4.y));
+        f[j + 2] = act_tc<ACT>(fmaf(__uint_as_float(v[j + 2]), s4.z, b4.z));
+        f[j + 3] = act_tc<ACT>(fmaf(__uint_as_float(v[j + 3]), s4.w, b4.w));
     }
 }
 
@@ -241,36 +250,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
     return t;
 }
 
-// One 32-column chunk of the epilogue for one accumulator row: +bias -> activation -> (+skip) -> store.
-__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const float* sbias, int col0,
-                                               long long drow, int n, int hp, int wp) {
-    float f[32];
-    uint4 rres[4];
-    if (p.res) {                                           // issue the skip-tile loads before the math that hides them
-        const uint4* rp = reinterpret_cast<const uint4*>(p.res + drow * p.res_ld + p.res_choff + col0);
-#pragma unroll
-        for (int j = 0; j < 4; j++) rres[j] = __ldg(rp + j);
-    }
-    if (p.act == 2) bias_act32<2>(v, sbias + col0, f);
-    else if (p.act == 1) bias_act32<1>(v, sbias + col0, f);
-    else bias_act32<0>(v, sbias + col0, f);
-    if (p.res) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&rres[j]);
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-                const float2 x = __half22float2(h2[t]);
-                f[j * 8 + t * 2] += x.x; f[j * 8 + t * 2 + 1] += x.y;
-            }
-        }
-    }
-    if (p.out_f32) {
-        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + drow * p.out_ld + p.out_choff + col0);
-#pragma unroll
-        for (int j = 0; j < 8; j++) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        return;
-    }
+__device__ __forceinline__ void pack_store8x4(__half* dst, const float (&f)[32]) {
     uint4 o[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
@@ -281,7 +261,59 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
         o[j].x = *reinterpret_cast<uint32_t*>(&h0); o[j].y = *reinterpret_cast<uint32_t*>(&h1);
         o[j].z = *reinterpret_cast<uint32_t*>(&h2); o[j].w = *reinterpret_cast<uint32_t*>(&h3);
     }
+    uint4* op = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; j++) op[j] = o[j];
+}
+
+__device__ __forceinline__ void add_half32(const uint4 (&r)[4], float (&f)[32]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const __half2* h2 = reinterpret_cast<const __half2*>(&r[j]);
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const float2 x = __half22float2(h2[t]);
+            f[j * 8 + t * 2] += x.x; f[j * 8 + t * 2 + 1] += x.y;
+        }
+    }
+}
+
+// One 32-column chunk of the epilogue for one accumulator row: (*scale) + bias -> activation -> (+skip) -> store.
+// Split precision: the skip tile is hi + lo, and the result is stored as hi = fp16(x), lo = fp16(x - hi).
+__device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const float* sbias, const float* sscale, int col0,
+                                               long long drow, int n, int hp, int wp) {
+    float f[32];
+    uint4 rres[4], rlo[4];
+    if (p.res) {                                           // issue the skip-tile loads before the math that hides them
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + drow * p.res_ld + p.res_choff + col0);
+#pragma unroll
+        for (int j = 0; j < 4; j++) rres[j] = __ldg(rp + j);
+        if (p.split) {
+            const uint4* rq = reinterpret_cast<const uint4*>(p.res_lo + drow * p.res_ld + p.res_choff + col0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) rlo[j] = __ldg(rq + j);
+        }
+    }
+    if (p.act == 2) bias_act32<2>(v, sbias + col0, sscale + col0, f);
+    else if (p.act == 1) bias_act32<1>(v, sbias + col0, sscale + col0, f);
+    else bias_act32<0>(v, sbias + col0, sscale + col0, f);
+    if (p.res) {
+        add_half32(rres, f);
+        if (p.split) add_half32(rlo, f);
+    }
+    if (p.out_f32) {
+        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + drow * p.out_ld + p.out_choff + col0);
+#pragma unroll
+        for (int j = 0; j < 8; j++) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        return;
+    }
+    float g[32];                                           // split: residual x - fp16(x), exactly representable difference
+    if (p.split) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) g[j] = f[j] - __half2float(__float2half_rn(f[j]));
+    }
     __half* ob = reinterpret_cast<__half*>(p.out);
+    __half* ol = reinterpret_cast<__half*>(p.out_lo);
     if (p.upsample) {
         const int DHp = 2 * (p.Hp - 2) + 2, DWp = 2 * (p.Wp - 2) + 2;
 #pragma unroll
@@ -289,14 +321,12 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
 #pragma unroll
             for (int dx = 0; dx < 2; dx++) {
                 const long long dr = ((long long)n * DHp + 2 * (hp - 1) + 1 + dy) * DWp + 2 * (wp - 1) + 1 + dx;
-                uint4* op = reinterpret_cast<uint4*>(ob + dr * p.out_ld + p.out_choff + col0);
-#pragma unroll
-                for (int j = 0; j < 4; j++) op[j] = o[j];
+                pack_store8x4(ob + dr * p.out_ld + p.out_choff + col0, f);
+                if (p.split) pack_store8x4(ol + dr * p.out_ld + p.out_choff + col0, g);
             }
     } else {
-        uint4* op = reinterpret_cast<uint4*>(ob + drow * p.out_ld + p.out_choff + col0);
-#pragma unroll
-        for (int j = 0; j < 4; j++) op[j] = o[j];
+        pack_store8x4(ob + drow * p.out_ld + p.out_choff + col0, f);
+        if (p.split) pack_store8x4(ol + drow * p.out_ld + p.out_choff + col0, g);
     }
 }
 
@@ -315,9 +345,10 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     const uint32_t base = (raw + 1023u) & ~1023u;
     const int S = p.stages;
     const int G = p.group;                                  // k-blocks per stage (modes 1,2)
+    const uint32_t SBYTES = p.split ? 2u * STAGE_BYTES : (uint32_t)STAGE_BYTES;   // split: [A_hi|B_hi|A_lo|B_lo]
     // modes 1,2: S stages of G x (A | B).   mode 3: patch_slots patches, then S stages of B only.
     // then: full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), pfull[4], pempty[4], bias[bias_n]
-    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : (uint32_t)(S * G) * STAGE_BYTES;
+    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : (uint32_t)(S * G) * SBYTES;
     const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);      // mode 3: first B stage
     const uint32_t bars = base + ring_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
@@ -341,7 +372,8 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
-    if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 128) sbias[i] = p.bias[i];
+    float* sscale = sbias + p.bias_n;
+    if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 128) { sbias[i] = p.bias[i]; sscale[i] = p.wscale ? p.wscale[i] : 1.0f; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -403,12 +435,12 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     mbar_wait_t(bar_empty + 8u * s, ph ^ 1u, dbg ? &w_empty : nullptr);
                     const uint32_t fb = bar_full + 8u * s;
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
-                    mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES));
+                    mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES) * (p.split ? 2u : 1u));
                     for (int kk = 0; kk < gcount; kk++) {
                         const int kb = kb0 + kk;
                         const int tap = kb / p.kb_per_tap;
                         const int c0 = (kb - tap * p.kb_per_tap) * BK;
-                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * STAGE_BYTES;
+                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * SBYTES;
                         if (p.mode == 1) {
                             int shift = 0;
                             if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
@@ -418,6 +450,18 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                             tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
                         }
                         tma_load_2d(sa + A_BYTES, &p.tmW, fb, kb * BK, tc.n0);
+                        if (p.split) {
+                            const uint32_t sl = sa + STAGE_BYTES;
+                            if (p.mode == 1) {
+                                int shift = 0;
+                                if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
+                                tma_load_2d(sl, &p.tmA_lo[0], fb, c0, (int)(tc.m0 + shift));
+                            } else {
+                                const int kh = tap / 3, kw = tap - kh * 3;
+                                tma_load_4d(sl, &p.tmA_lo[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
+                            }
+                            tma_load_2d(sl + A_BYTES, &p.tmW_lo, fb, kb * BK, tc.n0);
+                        }
                     }
                     if (it == 0) Y4_STAMP(2);
                 }
@@ -468,12 +512,24 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     if (it == 0) Y4_STAMP(4);
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
                     for (int kk = 0; kk < gcount; kk++) {
-                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * STAGE_BYTES;
+                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * SBYTES;
                         const uint64_t da = make_smem_desc<SWZ>(sa);
                         const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
+                        if (p.split) {
+                            // (a_hi + a_lo)(b_hi + b_lo) without the a_lo*b_lo term (2^-22 relative): small terms first
+                            const uint64_t la = make_smem_desc<SWZ>(sa + STAGE_BYTES);
+                            const uint64_t lb = make_smem_desc<SWZ>(sa + STAGE_BYTES + A_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) {
+                                umma_f16(tacc, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
+                                umma_f16(tacc, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), IDESC, 1u);
+                                umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, 1u);
+                            }
+                        } else {
 #pragma unroll
                         for (int k = 0; k < BK / 16; k++)
                             umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
+                        }
                     }
                     umma_commit(bar_empty + 8u * s);        // frees this smem stage once the MMAs have read it
                 }
@@ -519,11 +575,11 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             for (int c0 = 0; c0 < BN; c0 += 64) {
                 tmem_ld_wait(va);
                 tmem_ld32_issue(tacc + (uint32_t)(c0 + 32), vb);              // BN is a multiple of 64
-                if (valid && tc.n0 + c0 < p.cout_store) epilogue_chunk(p, va, sbias, tc.n0 + c0, drow, n, hp, wp);
+                if (valid && tc.n0 + c0 < p.cout_store) epilogue_chunk(p, va, sbias, sscale, tc.n0 + c0, drow, n, hp, wp);
                 __syncwarp();                               // tcgen05.ld / wait are .sync.aligned
                 tmem_ld_wait(vb);
                 if (c0 + 64 < BN) tmem_ld32_issue(tacc + (uint32_t)(c0 + 64), va);
-                if (valid && tc.n0 + c0 + 32 < p.cout_store) epilogue_chunk(p, vb, sbias, tc.n0 + c0 + 32, drow, n, hp, wp);
+                if (valid && tc.n0 + c0 + 32 < p.cout_store) epilogue_chunk(p, vb, sbias, sscale, tc.n0 + c0 + 32, drow, n, hp, wp);
                 __syncwarp();
             }
             // all TMEM reads of this stage have completed (last wait above): hand the stage back to the MMA warp
@@ -630,6 +686,8 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     memset(&p, 0, sizeof(p));
     P.tile_n = bn; P.bk = bk;
     p.bias = d.bias; p.out = d.out; p.res = reinterpret_cast<const __half*>(d.res);
+    p.split = d.split; p.out_lo = d.out_lo; p.res_lo = reinterpret_cast<const __half*>(d.res_lo); p.wscale = d.wscale;
+    if (d.split && (patch || bk != 64 && bk != 32)) return 0;
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
     p.act = d.act; p.out_f32 = d.out_f32; p.upsample = d.upsample;
     p.cout_store = d.out_f32 ? d.cout_pad : d.cout;
@@ -641,12 +699,14 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     const int in_Hp = d.in_H + 2, in_Wp = d.in_H + 2;
     P.in_Hp = in_Hp; P.in_Wp = in_Wp;
     char* in_base = reinterpret_cast<char*>(const_cast<void*>(d.in)) + (size_t)d.in_choff * 2;
+    char* in_base_lo = d.split ? reinterpret_cast<char*>(const_cast<void*>(d.in_lo)) + (size_t)d.in_choff * 2 : nullptr;
     // weights: [cout_pad][K] fp16
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d.cout_pad};
         cuuint64_t str[1] = {(cuuint64_t)K * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
         if (!encode_map(&p.tmW, const_cast<__half*>(d.w16), 2, dims, str, box, swz, err)) return -1;
+        if (d.split && !encode_map(&p.tmW_lo, const_cast<__half*>(d.w16_lo), 2, dims, str, box, swz, err)) return -1;
     }
     if (d.stride == 1) {
         P.kind = 1; p.mode = 1;
@@ -655,6 +715,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
         cuuint64_t str[1] = {(cuuint64_t)d.in_ld * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, 128};
         if (!encode_map(&p.tmA[0], in_base, 2, dims, str, box, swz, err)) return -1;
+        if (d.split && !encode_map(&p.tmA_lo[0], in_base_lo, 2, dims, str, box, swz, err)) return -1;
     } else {
         if (d.k != 3 || d.stride != 2 || d.upsample) return 0;
         P.kind = 2; p.mode = 2;
@@ -678,9 +739,13 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
                 cuuint64_t str[3] = {(cuuint64_t)2 * d.in_ld * 2, (cuuint64_t)2 * in_Wp * d.in_ld * 2, (cuuint64_t)in_Hp * in_Wp * d.in_ld * 2};
                 cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)bestTW, (cuuint32_t)bestTH, 1};
                 if (!encode_map(&p.tmA[ph * 2 + pw], b, 4, dims, str, box, swz, err)) return -1;
+                if (d.split) {
+                    char* bl = in_base_lo + ((size_t)ph * in_Wp + pw) * d.in_ld * 2;
+                    if (!encode_map(&p.tmA_lo[ph * 2 + pw], bl, 4, dims, str, box, swz, err)) return -1;
+                }
             }
     }
-    size_t stage_bytes = (size_t)128 * bk * 2 + (size_t)bn * bk * 2;
+    size_t stage_bytes = ((size_t)128 * bk * 2 + (size_t)bn * bk * 2) * (d.split ? 2 : 1);
     size_t ring_fixed = 0;
     if (!patch && getenv("Y4_FORCE_PATCH") && P.kind == 1 && d.k == 3 && bk == 64) { patch = 1; if (smem_budget_kb < 200) smem_budget_kb = 200; }
     if (patch) {
@@ -716,7 +781,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     P.stages = S; p.stages = S;
     p.n_tiles = (p.cout_store + bn - 1) / bn;
     p.bias_n = d.cout_pad;
-    P.smem = 1024 + ring_fixed + S * stage_bytes + 16 * S + 112 + 4 * (size_t)p.bias_n;
+    P.smem = 1024 + ring_fixed + S * stage_bytes + 16 * S + 112 + 8 * (size_t)p.bias_n;   // bias + weight-scale arrays
     if (P.smem > 220 * 1024) { *err = "smem budget exceeded"; return -1; }
     int cps = (int)((227 * 1024) / (P.smem + 1024));            // +1 KB: per-CTA reserved shared memory
     const int tmem_cols = 2 * bn;

@@ -166,6 +166,7 @@ struct Conv0Params {
     const float* w;        // [27][cout_pad] folded, K index = (kh*3+kw)*3 + c
     const float* bias;     // [cout_pad]
     __half* out;           // padded-flat (N, S+2, S+2, 32)
+    __half* out_lo;        // split precision: low-order plane (nullptr otherwise)
     int N, S, cout_pad;
 };
 
@@ -213,22 +214,32 @@ __global__ void __launch_bounds__(256) conv0_direct_kernel(Conv0Params p) {
         const int y = y0 + ty + half * 8, x = x0 + tx;
         if (y >= p.S || x >= p.S) continue;
         const float* a = half ? a1 : a0;
-        uint4 o[4];
+        uint4 o[4], ol[4];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-            __half2 h[4];
+            __half2 h[4], hl[4];
 #pragma unroll
             for (int t = 0; t < 4; t++) {
                 float u0 = a[8 * q + 2 * t] + bs[8 * q + 2 * t], u1 = a[8 * q + 2 * t + 1] + bs[8 * q + 2 * t + 1];
                 u0 = u0 > 0.f ? u0 : 0.1f * u0; u1 = u1 > 0.f ? u1 : 0.1f * u1;          // leaky (custom_layers.py:101 default act)
                 h[t] = __floats2half2_rn(u0, u1);
+                const float2 back = __half22float2(h[t]);
+                hl[t] = __floats2half2_rn(u0 - back.x, u1 - back.y);
             }
             o[q].x = *reinterpret_cast<uint32_t*>(&h[0]); o[q].y = *reinterpret_cast<uint32_t*>(&h[1]);
             o[q].z = *reinterpret_cast<uint32_t*>(&h[2]); o[q].w = *reinterpret_cast<uint32_t*>(&h[3]);
+            ol[q].x = *reinterpret_cast<uint32_t*>(&hl[0]); ol[q].y = *reinterpret_cast<uint32_t*>(&hl[1]);
+            ol[q].z = *reinterpret_cast<uint32_t*>(&hl[2]); ol[q].w = *reinterpret_cast<uint32_t*>(&hl[3]);
         }
-        uint4* op = reinterpret_cast<uint4*>(p.out + (((long long)n * Sp + y + 1) * Sp + x + 1) * 32);
+        const long long off = (((long long)n * Sp + y + 1) * Sp + x + 1) * 32;
+        uint4* op = reinterpret_cast<uint4*>(p.out + off);
 #pragma unroll
         for (int q = 0; q < 4; q++) op[q] = o[q];
+        if (p.out_lo) {
+            uint4* oq = reinterpret_cast<uint4*>(p.out_lo + off);
+#pragma unroll
+            for (int q = 0; q < 4; q++) oq[q] = ol[q];
+        }
     }
 }
 
@@ -313,6 +324,58 @@ __global__ void spp_kernel(SppParams p) {
     st_from_float(base + o, m13);
     st_from_float(base + o + p.C, m9);
     st_from_float(base + o + 2 * p.C, m5);
+}
+
+// split-precision SPP: values are hi + lo pairs; max picks one of its inputs, so re-splitting is exact
+__global__ void spp_split_kernel(SppParams p, void* buf_lo) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)p.N * p.H * p.W * p.C;
+    if (i >= total) return;
+    int c = (int)(i % p.C);
+    long long t = i / p.C;
+    int w = (int)(t % p.W); t /= p.W;
+    int h = (int)(t % p.H);
+    int n = (int)(t / p.H);
+    const int Hp = p.H + 2, Wp = p.W + 2;
+    __half* hi = reinterpret_cast<__half*>(p.buf);
+    __half* lo = reinterpret_cast<__half*>(buf_lo);
+    float m5 = -INFINITY, m9 = -INFINITY, m13 = -INFINITY;
+    for (int dy = -6; dy <= 6; dy++) {
+        int hh = h + dy;
+        if (hh < 0 || hh >= p.H) continue;
+        for (int dx = -6; dx <= 6; dx++) {
+            int ww = w + dx;
+            if (ww < 0 || ww >= p.W) continue;
+            const long long o = (((long long)n * Hp + hh + 1) * Wp + ww + 1) * p.ld + 3 * p.C + c;
+            float v = __half2float(hi[o]) + __half2float(lo[o]);
+            int ady = dy < 0 ? -dy : dy, adx = dx < 0 ? -dx : dx;
+            int d = ady > adx ? ady : adx;
+            m13 = fmaxf(m13, v);
+            if (d <= 4) m9 = fmaxf(m9, v);
+            if (d <= 2) m5 = fmaxf(m5, v);
+        }
+    }
+    const long long o = (((long long)n * Hp + h + 1) * Wp + w + 1) * p.ld + c;
+    const float vals[3] = {m13, m9, m5};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const __half a = __float2half_rn(vals[k]);
+        hi[o + k * p.C] = a;
+        lo[o + k * p.C] = __float2half_rn(vals[k] - __half2float(a));
+    }
+}
+
+__global__ void gather_view_split_kernel(const __half* hi, const __half* lo, float* dst, int N, int H, int W, int C, int ld, int choff) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long total = (long long)N * H * W * C;
+    if (i >= total) return;
+    int c = (int)(i % C);
+    long long t = i / C;
+    int w = (int)(t % W); t /= W;
+    int h = (int)(t % H);
+    int n = (int)(t / H);
+    const long long o = (((long long)n * (H + 2) + h + 1) * (W + 2) + w + 1) * ld + choff + c;
+    dst[i] = __half2float(hi[o]) + __half2float(lo[o]);
 }
 
 // splitmix64-style hash -> [0,1) with 24 random bits; bit-identical to oracle/y4_oracle.py:hash_uniform.

@@ -37,6 +37,7 @@ thread_local std::string g_create_error;
 
 struct Buf {
     void* ptr = nullptr;
+    void* ptr_lo = nullptr;    // split precision (Y4_PREC_FP16X3): low-order fp16 plane, same shape
     int H = 0, W = 0, C = 0;   // logical spatial dims, total channels (ld)
     int elt = 0;               // bytes per element
     size_t bytes = 0;
@@ -62,6 +63,8 @@ struct ConvOp {
     float* d_w32 = nullptr;    // [K][cout_pad]
     float* d_bias = nullptr;   // [cout_pad]
     __half* d_w16 = nullptr;   // [cout_pad][K]  (tcgen05 path)
+    __half* d_w16_lo = nullptr; // split precision: fp16(w*s - fp16(w*s)), s = per-cout power of two
+    float* d_wscale = nullptr;  // split precision: 1/s per cout (exact)
     __half* d_w16k32 = nullptr; // conv 0 only: [32][32], K zero-padded 27 -> 32 (conv0_tc.cuh)
     int kind = 0;              // 0 simt, 1 tc flat, 2 tc box
     TcConvPlan tc;             // tensor maps + tile config (conv_tc.cuh)
@@ -253,6 +256,10 @@ int alloc_buf(y4_engine* e, int H, int W, int C, int elt) {
     b.bytes = (size_t)e->cfg.max_batch * (H + 2) * (W + 2) * C * elt;
     if (cudaMalloc(&b.ptr, b.bytes) != cudaSuccess) return -1;
     if (cudaMemset(b.ptr, 0, b.bytes) != cudaSuccess) return -1;     // halo stays zero forever
+    if (e->cfg.precision == Y4_PREC_FP16X3 && elt == 2) {
+        if (cudaMalloc(&b.ptr_lo, b.bytes) != cudaSuccess) return -1;
+        if (cudaMemset(b.ptr_lo, 0, b.bytes) != cudaSuccess) return -1;
+    }
     e->bufs.push_back(b);
     return (int)e->bufs.size() - 1;
 }
@@ -377,6 +384,7 @@ void launch_spp(y4_engine* e, int batch) {
     long long total = (long long)batch * b.H * b.W * e->spp_C;
     unsigned blocks = (unsigned)((total + 255) / 256);
     if (e->elt == 4) spp_kernel<float><<<blocks, 256, 0, e->stream>>>(p);
+    else if (e->cfg.precision == Y4_PREC_FP16X3) spp_split_kernel<<<blocks, 256, 0, e->stream>>>(p, b.ptr_lo);
     else if (e->cfg.precision == Y4_PREC_FP16 && e->spp_C % 8 == 0)
         spp_half8_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, e->stream>>>(p);
     else spp_kernel<__half><<<blocks, 256, 0, e->stream>>>(p);
@@ -385,7 +393,7 @@ void launch_spp(y4_engine* e, int batch) {
 
 void launch_conv0_direct(y4_engine* e, const ConvOp& c, int batch) {
     const int S = e->cfg.img_size;
-    Conv0Params p{e->d_img, c.d_w32, c.d_bias, (__half*)e->bufs[c.out.buf].ptr, batch, S, c.cout_pad};
+    Conv0Params p{e->d_img, c.d_w32, c.d_bias, (__half*)e->bufs[c.out.buf].ptr, (__half*)e->bufs[c.out.buf].ptr_lo, batch, S, c.cout_pad};
     dim3 grid((unsigned)((S + 31) / 32), (unsigned)((S + 15) / 16), (unsigned)batch);
     conv0_direct_kernel<<<grid, 256, 0, e->stream>>>(p);
     e->launches++;
@@ -511,6 +519,28 @@ int upload_weights(y4_engine* e, const unsigned char* data, size_t nbytes) {
                     w16[(size_t)o * c.K + kidx] = __float2half_rn(v);
                 }
         off += 4ull * c.cout * c.cin * kk;
+        if (e->cfg.precision == Y4_PREC_FP16X3) {
+            // hi/lo split of the folded weights, scaled per cout by a power of two so that hi is O(1) and lo stays a
+            // normal fp16 number; the epilogue multiplies the accumulator by the (exact) inverse scale
+            std::vector<__half> wlo((size_t)c.cout_pad * c.K, __float2half(0.f));
+            std::vector<float> inv(c.cout_pad, 1.0f);
+            for (int o = 0; o < c.cout; o++) {
+                float mx = 0.f;
+                for (int k = 0; k < c.K; k++) mx = std::max(mx, std::fabs(w32[(size_t)k * c.cout_pad + o]));
+                int ex = 0;
+                if (mx > 0.f) std::frexp(mx, &ex);            // mx = m * 2^ex, m in [0.5, 1)
+                const float sc = std::ldexp(1.0f, -ex + 1);    // mx * sc in [1, 2)
+                inv[o] = std::ldexp(1.0f, ex - 1);
+                for (int k = 0; k < c.K; k++) {
+                    const float ws = w32[(size_t)k * c.cout_pad + o] * sc;
+                    const __half hi = __float2half_rn(ws);
+                    w16[(size_t)o * c.K + k] = hi;
+                    wlo[(size_t)o * c.K + k] = __float2half_rn(ws - __half2float(hi));
+                }
+            }
+            CUDA_TRY(e, cudaMemcpy(c.d_w16_lo, wlo.data(), wlo.size() * 2, cudaMemcpyHostToDevice));
+            CUDA_TRY(e, cudaMemcpy(c.d_wscale, inv.data(), inv.size() * 4, cudaMemcpyHostToDevice));
+        }
         CUDA_TRY(e, cudaMemcpy(c.d_w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(e, cudaMemcpy(c.d_w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
         if (c.d_w16k32) {
@@ -555,7 +585,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     if (cfg->max_boxes < 1 || cfg->max_boxes > kMaxBoxesCap || cfg->max_boxes * cfg->num_classes > kSelCap)
         return fail(nullptr, Y4_ERR_ARG, "max_boxes must be in [1,128] and max_boxes*num_classes <= 8192");
     if (cfg->max_batch < 1) return fail(nullptr, Y4_ERR_ARG, "max_batch must be >= 1");
-    if (cfg->precision < 0 || cfg->precision > 2) return fail(nullptr, Y4_ERR_ARG, "unknown precision");
+    if (cfg->precision < 0 || cfg->precision > 3) return fail(nullptr, Y4_ERR_ARG, "unknown precision");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, Y4_ERR_CUDA, "no CUDA device available (this engine has no CPU fallback)");
@@ -582,6 +612,11 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         CREATE_TRY(cudaMalloc(&c.d_w16, sizeof(__half) * c.K * c.cout_pad));
         if (c.raw_in && c.K == 27 && c.cout == 32) { CREATE_TRY(cudaMalloc(&c.d_w16k32, sizeof(__half) * 32 * 32)); CREATE_TRY(cudaMemset(c.d_w16k32, 0, sizeof(__half) * 32 * 32)); }
         CREATE_TRY(cudaMalloc(&c.d_bias, sizeof(float) * c.cout_pad));
+        if (cfg->precision == Y4_PREC_FP16X3) {
+            CREATE_TRY(cudaMalloc(&c.d_w16_lo, sizeof(__half) * c.K * c.cout_pad));
+            CREATE_TRY(cudaMalloc(&c.d_wscale, sizeof(float) * c.cout_pad));
+            CREATE_TRY(cudaMemset(c.d_wscale, 0, sizeof(float) * c.cout_pad));
+        }
     }
     for (int i = 0; i < 3; i++)
         CREATE_TRY(cudaMalloc(&e->d_user_heads[i], sizeof(float) * B * e->g[i] * e->g[i] * 3 * (5 + cfg->num_classes)));
@@ -600,7 +635,8 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     CREATE_TRY(cudaMalloc(&e->d_flush, e->flush_elems * sizeof(float4)));
     CREATE_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemBytes));
     // tcgen05 plans (tensor maps need the buffer addresses, which are now fixed)
-    if (cfg->precision == Y4_PREC_FP16) {
+    if (cfg->precision == Y4_PREC_FP16 || cfg->precision == Y4_PREC_FP16X3) {
+        const bool split = cfg->precision == Y4_PREC_FP16X3;
         for (auto& c : e->convs) {
             TcConvDesc d{};
             d.cin = c.cin; d.cout = c.cout; d.cout_pad = c.cout_pad; d.k = c.k; d.stride = c.stride; d.act = c.act;
@@ -610,11 +646,16 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             d.out = ob.ptr; d.out_ld = ob.C; d.out_choff = c.out.choff; d.out_f32 = c.out_f32; d.upsample = c.upsample;
             if (c.has_res) { const Buf& rb = e->bufs[c.res.buf]; d.res = rb.ptr; d.res_ld = rb.C; d.res_choff = c.res.choff; }
             d.w16 = c.d_w16; d.bias = c.d_bias;
+            if (split) {
+                d.split = 1; d.w16_lo = c.d_w16_lo; d.wscale = c.d_wscale; d.out_lo = ob.ptr_lo;
+                if (!c.raw_in) d.in_lo = e->bufs[c.in.buf].ptr_lo;
+                if (c.has_res) d.res_lo = e->bufs[c.res.buf].ptr_lo;
+            }
             std::string terr;
             if (c.raw_in && c.cin == 3 && c.cout == 32 && c.k == 3 && c.act == ACT_LEAKY && c.out.choff == 0 && ob.C == 32) {
                 // conv 0: tensor-core kernel (in-register im2col, kind 4) unless Y4_C0=direct (CUDA-core direct conv, kind 3)
                 const char* c0 = getenv("Y4_C0");
-                c.kind = (c0 && c0[0] == 'd') || !c.d_w16k32 ? 3 : 4;
+                c.kind = (c0 && c0[0] == 'd') || !c.d_w16k32 || split ? 3 : 4;   // split precision: fp32 direct conv writing hi + lo
                 continue;
             }
             int kind = tc_plan(d, &c.tc, &terr);
@@ -667,8 +708,8 @@ void y4_destroy(y4_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.first);
     if (e->comm) nccl().CommDestroy(e->comm);
-    for (auto& b : e->bufs) cudaFree(b.ptr);
-    for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_w16k32); cudaFree(c.d_bias); }
+    for (auto& b : e->bufs) { cudaFree(b.ptr); cudaFree(b.ptr_lo); }
+    for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_w16k32); cudaFree(c.d_w16_lo); cudaFree(c.d_wscale); cudaFree(c.d_bias); }
     cudaFree(e->d_img);
     for (int i = 0; i < 3; i++) cudaFree(e->d_user_heads[i]);
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
@@ -897,6 +938,7 @@ int y4_debug_run_conv(y4_engine* e, int32_t idx, int32_t batch, int32_t use_tc) 
         if (c.kind == 0) return fail(e, Y4_ERR_ARG, "conv has no tcgen05 plan");
         rc = run_conv(e, c, batch); if (rc) return rc;
     } else {
+        if (e->cfg.precision == Y4_PREC_FP16X3) return fail(e, Y4_ERR_ARG, "no CUDA-core kernel for split-precision buffers");
         launch_simt(e, c, batch);
     }
     CUDA_TRY(e, cudaGetLastError());
@@ -941,6 +983,7 @@ int64_t y4_debug_get_tensor(y4_engine* e, const char* name, int32_t batch, float
     CUDA_TRY(e, cudaMalloc(&tmp, total * sizeof(float)));
     unsigned blocks = (unsigned)((total + 255) / 256);
     if (b.elt == 4) gather_view_kernel<float><<<blocks, 256, 0, e->stream>>>((const float*)b.ptr, tmp, batch, v.H, v.W, v.C, b.C, v.choff);
+    else if (b.ptr_lo) gather_view_split_kernel<<<blocks, 256, 0, e->stream>>>((const __half*)b.ptr, (const __half*)b.ptr_lo, tmp, batch, v.H, v.W, v.C, b.C, v.choff);
     else gather_view_kernel<__half><<<blocks, 256, 0, e->stream>>>((const __half*)b.ptr, tmp, batch, v.H, v.W, v.C, b.C, v.choff);
     cudaError_t err = cudaMemcpyAsync(out, tmp, total * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
