@@ -48,6 +48,7 @@ struct TcParams {
     const __half* res;
     const __half* res_lo;
     int split;
+    float act_scale, inv_act_scale;   // split precision: stored activations = true value * 2^8 (keeps the lo plane out of fp16 subnormals)
     int out_ld, out_choff, res_ld, res_choff;
     int act, out_f32, upsample;
     int cout_store;              // columns >= cout_store are not written
@@ -298,8 +299,17 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
     else if (p.act == 1) bias_act32<1>(v, sbias + col0, sscale + col0, f);
     else bias_act32<0>(v, sbias + col0, sscale + col0, f);
     if (p.res) {
-        add_half32(rres, f);
-        if (p.split) add_half32(rlo, f);
+        if (p.split) {
+            float rs[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) rs[j] = 0.f;
+            add_half32(rlo, rs);
+            add_half32(rres, rs);
+#pragma unroll
+            for (int j = 0; j < 32; j++) f[j] = fmaf(rs[j], p.inv_act_scale, f[j]);      // skip tile is stored scaled
+        } else {
+            add_half32(rres, f);
+        }
     }
     if (p.out_f32) {
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + drow * p.out_ld + p.out_choff + col0);
@@ -310,7 +320,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
     float g[32];                                           // split: residual x - fp16(x), exactly representable difference
     if (p.split) {
 #pragma unroll
-        for (int j = 0; j < 32; j++) g[j] = f[j] - __half2float(__float2half_rn(f[j]));
+        for (int j = 0; j < 32; j++) { f[j] *= p.act_scale; g[j] = f[j] - __half2float(__float2half_rn(f[j])); }
     }
     __half* ob = reinterpret_cast<__half*>(p.out);
     __half* ol = reinterpret_cast<__half*>(p.out_lo);
@@ -686,6 +696,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     memset(&p, 0, sizeof(p));
     P.tile_n = bn; P.bk = bk;
     p.bias = d.bias; p.out = d.out; p.res = reinterpret_cast<const __half*>(d.res);
+    p.act_scale = d.split ? 256.f : 1.f; p.inv_act_scale = d.split ? 1.f / 256.f : 1.f;
     p.split = d.split; p.out_lo = d.out_lo; p.res_lo = reinterpret_cast<const __half*>(d.res_lo); p.wscale = d.wscale;
     if (d.split && (patch || bk != 64 && bk != 32)) return 0;
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;

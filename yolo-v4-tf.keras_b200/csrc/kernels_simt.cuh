@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(256) conv0_direct_kernel(Conv0Params p) {
             for (int t = 0; t < 4; t++) {
                 float u0 = a[8 * q + 2 * t] + bs[8 * q + 2 * t], u1 = a[8 * q + 2 * t + 1] + bs[8 * q + 2 * t + 1];
                 u0 = u0 > 0.f ? u0 : 0.1f * u0; u1 = u1 > 0.f ? u1 : 0.1f * u1;          // leaky (custom_layers.py:101 default act)
+                if (p.out_lo) { u0 *= 256.f; u1 *= 256.f; }                               // split planes are stored * 2^8
                 h[t] = __floats2half2_rn(u0, u1);
                 const float2 back = __half22float2(h[t]);
                 hl[t] = __floats2half2_rn(u0 - back.x, u1 - back.y);
@@ -365,7 +366,7 @@ __global__ void spp_split_kernel(SppParams p, void* buf_lo) {
     }
 }
 
-__global__ void gather_view_split_kernel(const __half* hi, const __half* lo, float* dst, int N, int H, int W, int C, int ld, int choff) {
+__global__ void gather_view_split_kernel(const __half* hi, const __half* lo, float* dst, int N, int H, int W, int C, int ld, int choff, float inv_scale) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * H * W * C;
     if (i >= total) return;
@@ -375,7 +376,7 @@ __global__ void gather_view_split_kernel(const __half* hi, const __half* lo, flo
     int h = (int)(t % H);
     int n = (int)(t / H);
     const long long o = (((long long)n * (H + 2) + h + 1) * (W + 2) + w + 1) * ld + choff + c;
-    dst[i] = __half2float(hi[o]) + __half2float(lo[o]);
+    dst[i] = (__half2float(hi[o]) + __half2float(lo[o])) * inv_scale;
 }
 
 // splitmix64-style hash -> [0,1) with 24 random bits; bit-identical to oracle/y4_oracle.py:hash_uniform.

@@ -529,8 +529,10 @@ int upload_weights(y4_engine* e, const unsigned char* data, size_t nbytes) {
                 for (int k = 0; k < c.K; k++) mx = std::max(mx, std::fabs(w32[(size_t)k * c.cout_pad + o]));
                 int ex = 0;
                 if (mx > 0.f) std::frexp(mx, &ex);            // mx = m * 2^ex, m in [0.5, 1)
-                const float sc = std::ldexp(1.0f, -ex + 1);    // mx * sc in [1, 2)
-                inv[o] = std::ldexp(1.0f, ex - 1);
+                // weights scaled into [1024, 2048): lo = w*2^-11 stays a NORMAL fp16 for all but |w| < max * 2^-13;
+                // activations are stored * 2^8 for the same reason (conv_tc.cuh act_scale); conv 0 reads the raw image
+                const float sc = std::ldexp(1.0f, -ex + 1 + 10);
+                inv[o] = std::ldexp(1.0f, ex - 1 - 10) * (c.raw_in ? 1.0f : 1.0f / 256.0f);
                 for (int k = 0; k < c.K; k++) {
                     const float ws = w32[(size_t)k * c.cout_pad + o] * sc;
                     const __half hi = __float2half_rn(ws);
@@ -983,7 +985,7 @@ int64_t y4_debug_get_tensor(y4_engine* e, const char* name, int32_t batch, float
     CUDA_TRY(e, cudaMalloc(&tmp, total * sizeof(float)));
     unsigned blocks = (unsigned)((total + 255) / 256);
     if (b.elt == 4) gather_view_kernel<float><<<blocks, 256, 0, e->stream>>>((const float*)b.ptr, tmp, batch, v.H, v.W, v.C, b.C, v.choff);
-    else if (b.ptr_lo) gather_view_split_kernel<<<blocks, 256, 0, e->stream>>>((const __half*)b.ptr, (const __half*)b.ptr_lo, tmp, batch, v.H, v.W, v.C, b.C, v.choff);
+    else if (b.ptr_lo) gather_view_split_kernel<<<blocks, 256, 0, e->stream>>>((const __half*)b.ptr, (const __half*)b.ptr_lo, tmp, batch, v.H, v.W, v.C, b.C, v.choff, 1.0f / 256.0f);
     else gather_view_kernel<__half><<<blocks, 256, 0, e->stream>>>((const __half*)b.ptr, tmp, batch, v.H, v.W, v.C, b.C, v.choff);
     cudaError_t err = cudaMemcpyAsync(out, tmp, total * sizeof(float), cudaMemcpyDeviceToHost, e->stream);
     if (err == cudaSuccess) err = cudaStreamSynchronize(e->stream);
