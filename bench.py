@@ -126,7 +126,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--size', type=int, default=608)
     ap.add_argument('--batch', type=int, default=32, help='images per GPU per step')
-    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32'])
+    ap.add_argument('--precision', default='fp16', choices=['fp16', 'fp32', 'fp16x3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
@@ -148,7 +148,7 @@ def main():
     from y4b200 import binding
 
     S, B = args.size, args.batch
-    prec = y4b200.PREC_FP16 if args.precision == 'fp16' else y4b200.PREC_FP32
+    prec = {'fp16': y4b200.PREC_FP16, 'fp32': y4b200.PREC_FP32, 'fp16x3': y4b200.PREC_FP16X3}[args.precision]
     eng = y4b200.Engine(img_size=S, max_batch=B, precision=prec, device=local)
     W = O.synth_weights(seed=1)
     eng.load_darknet_bytes(W.to_darknet_bytes())
@@ -232,7 +232,7 @@ def main():
         return
     line = {'metric': METRIC, 'value': value, 'unit': 'images/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f16' if args.precision == 'fp16' else 'f32', 'data': 'synthetic',
+            'dtype': {'fp16': 'f16', 'fp32': 'f32', 'fp16x3': 'f16x3 (hi+lo fp16 operands, fp32 accumulate)'}[args.precision], 'data': 'synthetic',
             'config': {'workload': f'configs[1]: yolov4 CSPDarknet53+SPP+PANet forward + 3-scale decode + per-class NMS, '
                                    f'batch {B}/GPU, {S}x{S}, 80 classes, seeded random weights/images',
                        'l2': 'activations written+read per step (~7.3 GB at batch 32) >> 126 MB L2; no flush needed',
