@@ -160,44 +160,74 @@ struct NmsParams {
     int* overflow;         // set to 1 if any image exceeded kCandCap
 };
 
-// One CTA per image: sort candidates (class asc, score desc) -> one warp per class runs the greedy
-// suppression (each lane tests the candidate against a strided subset of the already-selected boxes,
-// warp vote) -> sort the survivors by score -> top max_boxes, clipped to [0,1], zero padded.
+// One CTA per image.  Candidates are grouped by class with a counting sort (histogram + scatter), each class segment
+// is ordered (score desc, box asc) by a warp rank-sort (segments are short: ~candidates/80), one warp per class runs the
+// greedy suppression (boxes fetched 32 at a time and broadcast by shuffle; every lane tests the candidate against a
+// strided subset of the already-selected boxes, warp vote), and the per-class winner lists - already in score order -
+// are merged by an 80-way tournament (score desc, class asc, box asc) into the top max_boxes, clipped to [0,1].
+// A class with more than kRankSortMax candidates falls back to one full bitonic sort of the keys.
+constexpr int kRankSortMax = 256;
+
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
     extern __shared__ __align__(16) unsigned char nms_smem[];
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(nms_smem);
-    unsigned long long* sel = keys + kCandCap;
-    float4* wbox = reinterpret_cast<float4*>(sel + kSelCap);        // [32 warps][kMaxBoxesCap]
-    __shared__ int selcount;
+    unsigned long long* bufA = reinterpret_cast<unsigned long long*>(nms_smem);      // keys, finally class-sorted
+    unsigned long long* bufB = bufA + kCandCap;                                       // scatter target, then winner lists
+    float4* wbox = reinterpret_cast<float4*>(bufB + kSelCap);                         // [32 warps][kMaxBoxesCap]
+    __shared__ int hist[256], start[257], cursor[256], nwin[256];
+    __shared__ int big;
 
     const int img = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int cnt = p.cand_count[img];
     if (cnt > kCandCap) { if (tid == 0) *p.overflow = 1; cnt = kCandCap; }
-    int P = 32;
-    while (P < cnt) P <<= 1;
-    for (int i = tid; i < P; i += blockDim.x)
-        keys[i] = i < cnt ? p.cand_keys[(long long)img * kCandCap + i] : ~0ull;
-    if (tid == 0) selcount = 0;
+    if (tid < 256) { hist[tid] = 0; nwin[tid] = 0; }
+    if (tid == 0) big = 0;
     __syncthreads();
-    bitonic_sort_smem(keys, P);
+    for (int i = tid; i < cnt; i += blockDim.x) {
+        const unsigned long long k = p.cand_keys[(long long)img * kCandCap + i];
+        bufA[i] = k;
+        atomicAdd(&hist[(int)(k >> 56)], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0, mx = 0;
+        for (int c = 0; c < 256; c++) { start[c] = acc; cursor[c] = acc; acc += hist[c]; mx = hist[c] > mx ? hist[c] : mx; }
+        start[256] = acc;
+        big = mx > kRankSortMax;
+    }
+    __syncthreads();
+    if (big) {
+        int P = 32;
+        while (P < cnt) P <<= 1;
+        for (int i = cnt + tid; i < P; i += blockDim.x) bufA[i] = ~0ull;
+        __syncthreads();
+        bitonic_sort_smem(bufA, P);
+    } else {
+        for (int i = tid; i < cnt; i += blockDim.x) {
+            const unsigned long long k = bufA[i];
+            bufB[atomicAdd(&cursor[(int)(k >> 56)], 1)] = k;
+        }
+        __syncthreads();
+        // rank sort inside each class segment: keys are unique (box index), rank = #smaller keys
+        for (int c = warp; c < p.nc; c += (kNmsThreads >> 5)) {
+            const int lo = start[c], L = hist[c];
+            for (int i = lane; i < L; i += 32) {
+                const unsigned long long k = bufB[lo + i];
+                int r = 0;
+                for (int j = 0; j < L; j++) r += bufB[lo + j] < k;
+                bufA[lo + r] = k;
+            }
+        }
+        __syncthreads();
+    }
+    const unsigned long long* keys = bufA;
 
     const float4* boxes = p.boxes + (long long)img * p.N;
     float4* mybox = wbox + warp * kMaxBoxesCap;
     for (int c = warp; c < p.nc; c += (kNmsThreads >> 5)) {
-        // segment of class c: lower_bound on the class field
-        int lo, hi;
-        {
-            const unsigned long long klo = (unsigned long long)c << 56, khi = (unsigned long long)(c + 1) << 56;
-            int a = 0, b = cnt;
-            while (a < b) { int m = (a + b) >> 1; if (keys[m] < klo) a = m + 1; else b = m; }
-            lo = a; b = cnt;
-            while (a < b) { int m = (a + b) >> 1; if (keys[m] < khi) a = m + 1; else b = m; }
-            hi = a;
-        }
+        const int lo = start[c], hi = start[c] + hist[c];
+        unsigned long long* win = bufB + (size_t)c * p.max_boxes;       // winners of class c, in score order
         int nsel = 0;
-        // candidates are visited in score order; their boxes are fetched 32 at a time (one global round trip per
-        // batch instead of one per candidate) and broadcast lane by lane
         for (int base = lo; base < hi && nsel < p.max_boxes; base += 32) {
             const int mine = base + lane;
             unsigned long long mykey = 0ull;
@@ -215,30 +245,62 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
                     if (lane == 0) {
                         mybox[nsel] = b;
                         const float score = __uint_as_float(~(unsigned)((key >> 24) & 0xFFFFFFFFull));
-                        sel[atomicAdd(&selcount, 1)] = merge_key(c, score, (int)(key & 0xFFFFFFull));
+                        win[nsel] = merge_key(c, score, (int)(key & 0xFFFFFFull));
                     }
                     nsel++;
                     __syncwarp();
                 }
             }
         }
+        if (lane == 0) nwin[c] = nsel;
     }
     __syncthreads();
-    const int ns = selcount;
-    int P2 = 32;
-    while (P2 < ns) P2 <<= 1;
-    for (int i = ns + tid; i < P2; i += blockDim.x) sel[i] = ~0ull;
-    __syncthreads();
-    bitonic_sort_smem(sel, P2);
 
-    const int nvalid = ns < p.max_boxes ? ns : p.max_boxes;
+    // 80-way tournament by warp 0: lane l owns classes l, l+32, ...; smallest merge key wins each round
+    __shared__ unsigned long long outkeys[kMaxBoxesCap];
+    __shared__ int nout;
+    if (warp == 0) {
+        int head[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) head[q] = 0;
+        int produced = 0;
+        while (produced < p.max_boxes) {
+            unsigned long long best = ~0ull;
+            int bq = -1;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int c = lane + 32 * q;
+                if (c < p.nc && head[q] < nwin[c]) {
+                    const unsigned long long k = bufB[(size_t)c * p.max_boxes + head[q]];
+                    if (k < best) { best = k; bq = q; }
+                }
+            }
+            unsigned long long wmin = best;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(0xffffffffu, wmin, o);
+                wmin = other < wmin ? other : wmin;
+            }
+            if (wmin == ~0ull) break;
+            if (best == wmin && bq >= 0) {                  // keys are unique: exactly one lane owns the winner
+#pragma unroll
+                for (int q = 0; q < 8; q++) head[q] += (q == bq);
+                outkeys[produced] = wmin;
+            }
+            produced++;
+        }
+        if (lane == 0) nout = produced;
+    }
+    __syncthreads();
+
+    const int nvalid = nout;
     if (tid == 0) p.out_valid[img] = nvalid;
     for (int k = tid; k < p.max_boxes; k += blockDim.x) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         float score = 0.f, cls = 0.f;
         int idx = -1;
         if (k < nvalid) {
-            const unsigned long long key = sel[k];
+            const unsigned long long key = outkeys[k];
             idx = (int)(key & 0xFFFFFFull);
             cls = (float)((key >> 24) & 0xFFull);
             score = __uint_as_float(~(unsigned)(key >> 32));
