@@ -281,6 +281,7 @@ __device__ __forceinline__ void add_half32(const uint4 (&r)[4], float (&f)[32]) 
 
 // One 32-column chunk of the epilogue for one accumulator row: (*scale) + bias -> activation -> (+skip) -> store.
 // Split precision: the skip tile is hi + lo, and the result is stored as hi = fp16(x), lo = fp16(x - hi).
+template <bool SPLIT>
 __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t (&v)[32], const float* sbias, const float* sscale, int col0,
                                                long long drow, int n, int hp, int wp) {
     float f[32];
@@ -289,7 +290,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
         const uint4* rp = reinterpret_cast<const uint4*>(p.res + drow * p.res_ld + p.res_choff + col0);
 #pragma unroll
         for (int j = 0; j < 4; j++) rres[j] = __ldg(rp + j);
-        if (p.split) {
+        if (SPLIT) {
             const uint4* rq = reinterpret_cast<const uint4*>(p.res_lo + drow * p.res_ld + p.res_choff + col0);
 #pragma unroll
             for (int j = 0; j < 4; j++) rlo[j] = __ldg(rq + j);
@@ -299,7 +300,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
     else if (p.act == 1) bias_act32<1>(v, sbias + col0, sscale + col0, f);
     else bias_act32<0>(v, sbias + col0, sscale + col0, f);
     if (p.res) {
-        if (p.split) {
+        if (SPLIT) {
             float rs[32];
 #pragma unroll
             for (int j = 0; j < 32; j++) rs[j] = 0.f;
@@ -318,7 +319,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
         return;
     }
     float g[32];                                           // split: residual x - fp16(x), exactly representable difference
-    if (p.split) {
+    if (SPLIT) {
 #pragma unroll
         for (int j = 0; j < 32; j++) { f[j] *= p.act_scale; g[j] = f[j] - __half2float(__float2half_rn(f[j])); }
     }
@@ -332,15 +333,15 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
             for (int dx = 0; dx < 2; dx++) {
                 const long long dr = ((long long)n * DHp + 2 * (hp - 1) + 1 + dy) * DWp + 2 * (wp - 1) + 1 + dx;
                 pack_store8x4(ob + dr * p.out_ld + p.out_choff + col0, f);
-                if (p.split) pack_store8x4(ol + dr * p.out_ld + p.out_choff + col0, g);
+                if (SPLIT) pack_store8x4(ol + dr * p.out_ld + p.out_choff + col0, g);
             }
     } else {
         pack_store8x4(ob + drow * p.out_ld + p.out_choff + col0, f);
-        if (p.split) pack_store8x4(ol + drow * p.out_ld + p.out_choff + col0, g);
+        if (SPLIT) pack_store8x4(ol + drow * p.out_ld + p.out_choff + col0, g);
     }
 }
 
-template <int BN, int BK>
+template <int BN, int BK, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int SWZ = BK * 2;
     constexpr int A_BYTES = 128 * BK * 2;
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     const uint32_t base = (raw + 1023u) & ~1023u;
     const int S = p.stages;
     const int G = p.group;                                  // k-blocks per stage (modes 1,2)
-    const uint32_t SBYTES = p.split ? 2u * STAGE_BYTES : (uint32_t)STAGE_BYTES;   // split: [A_hi|B_hi|A_lo|B_lo]
+    const uint32_t SBYTES = SPLIT ? 2u * STAGE_BYTES : (uint32_t)STAGE_BYTES;   // split: [A_hi|B_hi|A_lo|B_lo]
     // modes 1,2: S stages of G x (A | B).   mode 3: patch_slots patches, then S stages of B only.
     // then: full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), pfull[4], pempty[4], bias[bias_n]
     const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : (uint32_t)(S * G) * SBYTES;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     mbar_wait_t(bar_empty + 8u * s, ph ^ 1u, dbg ? &w_empty : nullptr);
                     const uint32_t fb = bar_full + 8u * s;
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
-                    mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES) * (p.split ? 2u : 1u));
+                    mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES) * (SPLIT ? 2u : 1u));
                     for (int kk = 0; kk < gcount; kk++) {
                         const int kb = kb0 + kk;
                         const int tap = kb / p.kb_per_tap;
@@ -460,7 +461,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                             tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
                         }
                         tma_load_2d(sa + A_BYTES, &p.tmW, fb, kb * BK, tc.n0);
-                        if (p.split) {
+                        if (SPLIT) {
                             const uint32_t sl = sa + STAGE_BYTES;
                             if (p.mode == 1) {
                                 int shift = 0;
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                         const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * SBYTES;
                         const uint64_t da = make_smem_desc<SWZ>(sa);
                         const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
-                        if (p.split) {
+                        if (SPLIT) {
                             // (a_hi + a_lo)(b_hi + b_lo) without the a_lo*b_lo term (2^-22 relative): small terms first
                             const uint64_t la = make_smem_desc<SWZ>(sa + STAGE_BYTES);
                             const uint64_t lb = make_smem_desc<SWZ>(sa + STAGE_BYTES + A_BYTES);
@@ -585,11 +586,11 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             for (int c0 = 0; c0 < BN; c0 += 64) {
                 tmem_ld_wait(va);
                 tmem_ld32_issue(tacc + (uint32_t)(c0 + 32), vb);              // BN is a multiple of 64
-                if (valid && tc.n0 + c0 < p.cout_store) epilogue_chunk(p, va, sbias, sscale, tc.n0 + c0, drow, n, hp, wp);
+                if (valid && tc.n0 + c0 < p.cout_store) epilogue_chunk<SPLIT>(p, va, sbias, sscale, tc.n0 + c0, drow, n, hp, wp);
                 __syncwarp();                               // tcgen05.ld / wait are .sync.aligned
                 tmem_ld_wait(vb);
                 if (c0 + 64 < BN) tmem_ld32_issue(tacc + (uint32_t)(c0 + 64), va);
-                if (valid && tc.n0 + c0 + 32 < p.cout_store) epilogue_chunk(p, vb, sbias, sscale, tc.n0 + c0 + 32, drow, n, hp, wp);
+                if (valid && tc.n0 + c0 + 32 < p.cout_store) epilogue_chunk<SPLIT>(p, vb, sbias, sscale, tc.n0 + c0 + 32, drow, n, hp, wp);
                 __syncwarp();
             }
             // all TMEM reads of this stage have completed (last wait above): hand the stage back to the MMA warp
@@ -635,16 +636,20 @@ inline bool encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* d
     return true;
 }
 
-template <int BN, int BK>
-inline cudaError_t launch_inst(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
+template <int BN, int BK, bool SPLIT>
+inline cudaError_t launch_inst2(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
     static size_t configured = 0;
     if (pl.smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
         if (e != cudaSuccess) return e;
         configured = 220 * 1024;
     }
-    conv_tc_kernel<BN, BK><<<grid, kTcThreads, pl.smem, st>>>(pl.p);
+    conv_tc_kernel<BN, BK, SPLIT><<<grid, kTcThreads, pl.smem, st>>>(pl.p);
     return cudaGetLastError();
+}
+template <int BN, int BK>
+inline cudaError_t launch_inst(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
+    return pl.p.split ? launch_inst2<BN, BK, true>(pl, grid, st) : launch_inst2<BN, BK, false>(pl, grid, st);
 }
 
 inline int sm_count() {
@@ -799,6 +804,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     if (cps > 512 / tmem_cols) cps = 512 / tmem_cols;            // two accumulator stages per CTA must all fit in TMEM
     if (cps > 2) cps = 2;                                        // register file: ~140 regs x 192 threads
     if (cps < 1) cps = 1;
+    if (d.split) cps = 1;                                       // split kernels use > 170 registers/thread
     P.ctas_per_sm = cps;
     *pl = P;
     return P.kind;
