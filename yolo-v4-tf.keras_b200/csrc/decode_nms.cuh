@@ -165,7 +165,7 @@ struct NmsParams {
 // greedy suppression (boxes fetched 32 at a time and broadcast by shuffle; every lane tests the candidate against a
 // strided subset of the already-selected boxes, warp vote), and the per-class winner lists - already in score order -
 // are merged by an 80-way tournament (score desc, class asc, box asc) into the top max_boxes, clipped to [0,1].
-// A class with more than kRankSortMax candidates falls back to one full bitonic sort of the keys.
+// Segments longer than kRankSortMax are rank-sorted by the whole CTA (cost ~ L^2 / 1024 per thread).
 constexpr int kRankSortMax = 256;
 
 __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
@@ -196,30 +196,36 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
         big = mx > kRankSortMax;
     }
     __syncthreads();
-    if (big) {
-        int P = 32;
-        while (P < cnt) P <<= 1;
-        for (int i = cnt + tid; i < P; i += blockDim.x) bufA[i] = ~0ull;
-        __syncthreads();
-        bitonic_sort_smem(bufA, P);
-    } else {
-        for (int i = tid; i < cnt; i += blockDim.x) {
-            const unsigned long long k = bufA[i];
-            bufB[atomicAdd(&cursor[(int)(k >> 56)], 1)] = k;
+    for (int i = tid; i < cnt; i += blockDim.x) {
+        const unsigned long long k = bufA[i];
+        bufB[atomicAdd(&cursor[(int)(k >> 56)], 1)] = k;
+    }
+    __syncthreads();
+    // rank sort inside each class segment: keys are unique (box index), rank = #smaller keys.
+    // short segments: one warp each; segments longer than kRankSortMax: the whole CTA, one segment after the other
+    for (int c = warp; c < p.nc; c += (kNmsThreads >> 5)) {
+        const int lo = start[c], L = hist[c];
+        if (L > kRankSortMax) continue;
+        for (int i = lane; i < L; i += 32) {
+            const unsigned long long k = bufB[lo + i];
+            int r = 0;
+            for (int j = 0; j < L; j++) r += bufB[lo + j] < k;
+            bufA[lo + r] = k;
         }
-        __syncthreads();
-        // rank sort inside each class segment: keys are unique (box index), rank = #smaller keys
-        for (int c = warp; c < p.nc; c += (kNmsThreads >> 5)) {
+    }
+    if (big) {
+        for (int c = 0; c < p.nc; c++) {
             const int lo = start[c], L = hist[c];
-            for (int i = lane; i < L; i += 32) {
+            if (L <= kRankSortMax) continue;                     // block-uniform
+            for (int i = tid; i < L; i += blockDim.x) {
                 const unsigned long long k = bufB[lo + i];
                 int r = 0;
                 for (int j = 0; j < L; j++) r += bufB[lo + j] < k;
                 bufA[lo + r] = k;
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
     const unsigned long long* keys = bufA;
 
     const float4* boxes = p.boxes + (long long)img * p.N;
