@@ -164,7 +164,7 @@ struct NmsParams {
 // is ordered (score desc, box asc) by a warp rank-sort (segments are short: ~candidates/80), one warp per class runs the
 // greedy suppression (boxes fetched 32 at a time and broadcast by shuffle; every lane tests the candidate against a
 // strided subset of the already-selected boxes, warp vote), and the per-class winner lists - already in score order -
-// are merged by an 80-way tournament (score desc, class asc, box asc) into the top max_boxes, clipped to [0,1].
+// are merged by global ranking (score desc, class asc, box asc) into the top max_boxes, clipped to [0,1].
 // Segments longer than kRankSortMax are rank-sorted by the whole CTA (cost ~ L^2 / 1024 per thread).
 constexpr int kRankSortMax = 256;
 
@@ -191,8 +191,8 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
     __syncthreads();
     if (tid == 0) {
         int acc = 0, mx = 0;
-        for (int c = 0; c < 256; c++) { start[c] = acc; cursor[c] = acc; acc += hist[c]; mx = hist[c] > mx ? hist[c] : mx; }
-        start[256] = acc;
+        for (int c = 0; c < p.nc; c++) { start[c] = acc; cursor[c] = acc; acc += hist[c]; mx = hist[c] > mx ? hist[c] : mx; }
+        start[p.nc] = acc;
         big = mx > kRankSortMax;
     }
     __syncthreads();
@@ -262,41 +262,28 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
     }
     __syncthreads();
 
-    // 80-way tournament by warp 0: lane l owns classes l, l+32, ...; smallest merge key wins each round
+    // merge: compact the per-class winner lists, then every winner computes its global rank (number of smaller merge
+    // keys = score desc, class asc, box asc; keys are unique) and the first max_boxes ranks are the output order
     __shared__ unsigned long long outkeys[kMaxBoxesCap];
     __shared__ int nout;
-    if (warp == 0) {
-        int head[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) head[q] = 0;
-        int produced = 0;
-        while (produced < p.max_boxes) {
-            unsigned long long best = ~0ull;
-            int bq = -1;
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-                const int c = lane + 32 * q;
-                if (c < p.nc && head[q] < nwin[c]) {
-                    const unsigned long long k = bufB[(size_t)c * p.max_boxes + head[q]];
-                    if (k < best) { best = k; bq = q; }
-                }
-            }
-            unsigned long long wmin = best;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, wmin, o);
-                wmin = other < wmin ? other : wmin;
-            }
-            if (wmin == ~0ull) break;
-            if (best == wmin && bq >= 0) {                  // keys are unique: exactly one lane owns the winner
-#pragma unroll
-                for (int q = 0; q < 8; q++) head[q] += (q == bq);
-                outkeys[produced] = wmin;
-            }
-            produced++;
-        }
-        if (lane == 0) nout = produced;
+    if (tid == 0) {
+        int acc = 0;
+        for (int c = 0; c < p.nc; c++) { cursor[c] = acc; acc += nwin[c]; }
+        nout = acc;
     }
+    __syncthreads();
+    const int ntot = nout;
+    for (int c = warp; c < p.nc; c += (kNmsThreads >> 5))
+        for (int i = lane; i < nwin[c]; i += 32) bufA[cursor[c] + i] = bufB[(size_t)c * p.max_boxes + i];
+    __syncthreads();
+    for (int i = tid; i < ntot; i += blockDim.x) {
+        const unsigned long long k = bufA[i];
+        int r = 0;
+        for (int j = 0; j < ntot && r < p.max_boxes; j++) r += bufA[j] < k;
+        if (r < p.max_boxes) outkeys[r] = k;
+    }
+    __syncthreads();
+    if (tid == 0) nout = ntot < p.max_boxes ? ntot : p.max_boxes;
     __syncthreads();
 
     const int nvalid = nout;
