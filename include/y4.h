@@ -101,6 +101,14 @@ int  y4_decode_nms(y4_engine* e, const float* head_s, const float* head_m, const
                    int32_t batch, float iou_threshold, float score_threshold,
                    float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx);
 
+/* ---- pipelined host path (batched callers such as export_prediction, models.py:141-179) ------------------------- */
+/* y4_submit enqueues H2D of `imgs` (host, ideally pinned: y4_host_alloc) on a copy stream, then forward + decode + NMS and
+ * the D2H of the results into pinned staging, and returns immediately; y4_collect blocks until the OLDEST outstanding
+ * submit has finished and copies its results out.  Up to two submits may be outstanding, so the H2D of batch i+1
+ * overlaps the compute of batch i.  Same outputs as y4_predict. */
+int  y4_submit(y4_engine* e, const float* imgs, int32_t batch);
+int  y4_collect(y4_engine* e, int32_t batch, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx);
+
 /* ---- device-resident path (benchmarks, data-parallel serving) ------------------------------------- */
 /* Fill the engine's device input with synthetic images: pixel value = hash(seed, global element index),
  * image i depends only on (seed, first_index + i) so results do not depend on how images are sharded. */

@@ -162,3 +162,28 @@ def test_error_paths(weights):
     with pytest.raises(y4b200.Y4Error):
         eng.predict(np.zeros((2, 64, 64, 3), np.float32))   # batch > max_batch
     eng.close()
+
+
+def test_submit_collect_matches_predict(weights):
+    """Pipelined host path (y4_submit / y4_collect, depth 2) returns exactly what the blocking y4_predict returns,
+    in submission order."""
+    import y4b200
+    import y4_oracle as O
+    W, blob = weights
+    S, B = 160, 2
+    eng = y4b200.Engine(img_size=S, max_batch=B, precision=y4b200.PREC_FP16)
+    eng.load_darknet_bytes(blob)
+    batches = [O.synth_images(0, i * B, B, S) for i in range(4)]
+    ref = [eng.predict(x, with_indices=True) for x in batches]
+    got = []
+    eng.submit(batches[0])
+    for i in range(1, 4):
+        eng.submit(batches[i])
+        got.append(eng.collect(with_indices=True))
+    got.append(eng.collect(with_indices=True))
+    with pytest.raises(y4b200.Y4Error):
+        eng.collect()
+    for r, g in zip(ref, got):
+        for a, b in zip(r, g):
+            assert np.array_equal(a, b)
+    eng.close()

@@ -35,7 +35,7 @@ class Y4LayerInfo(C.Structure):
 
 EXPORTS = [
     'y4_default_config', 'y4_create', 'y4_destroy', 'y4_last_error', 'y4_load_darknet',
-    'y4_load_darknet_from_memory', 'y4_predict', 'y4_forward_heads', 'y4_decode_nms', 'y4_synth_fill',
+    'y4_load_darknet_from_memory', 'y4_predict', 'y4_submit', 'y4_collect', 'y4_forward_heads', 'y4_decode_nms', 'y4_synth_fill',
     'y4_run_resident', 'y4_run_forward_resident', 'y4_run_decode_nms_resident', 'y4_upload_heads',
     'y4_fetch_results', 'y4_sync', 'y4_timer_begin', 'y4_timer_end', 'y4_flush_l2', 'y4_launch_count',
     'y4_profile_layers', 'y4_host_alloc', 'y4_host_free', 'y4_num_layers', 'y4_describe_layer', 'y4_num_boxes',
@@ -63,6 +63,8 @@ def load_library():
     lib.y4_load_darknet.argtypes = [vp, C.c_char_p]
     lib.y4_load_darknet_from_memory.argtypes = [vp, vp, C.c_size_t]
     lib.y4_predict.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
+    lib.y4_submit.argtypes = [vp, vp, C.c_int32]
+    lib.y4_collect.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.y4_forward_heads.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
     lib.y4_decode_nms.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_float, C.c_float, vp, vp, vp, vp, vp]
     lib.y4_synth_fill.argtypes = [vp, C.c_uint64, C.c_int64, C.c_int32]
@@ -184,6 +186,19 @@ class Engine:
         b = imgs.shape[0]
         boxes, scores, classes, valid, idx = self._alloc_out(b)
         self._chk(self._lib.y4_predict(self._h, _ptr(imgs), b, _ptr(boxes), _ptr(scores), _ptr(classes), _ptr(valid), _ptr(idx)))
+        return (boxes, scores, classes, valid, idx) if with_indices else [boxes, scores, classes, valid]
+
+    def submit(self, imgs):
+        """Pipelined path: enqueue one batch (keep `imgs` alive and unmodified until the matching collect())."""
+        imgs = self._imgs(imgs)
+        self._chk(self._lib.y4_submit(self._h, _ptr(imgs), imgs.shape[0]))
+        self._inflight = getattr(self, '_inflight', []) + [imgs]
+
+    def collect(self, with_indices=False):
+        imgs = self._inflight.pop(0)
+        b = imgs.shape[0]
+        boxes, scores, classes, valid, idx = self._alloc_out(b)
+        self._chk(self._lib.y4_collect(self._h, b, _ptr(boxes), _ptr(scores), _ptr(classes), _ptr(valid), _ptr(idx)))
         return (boxes, scores, classes, valid, idx) if with_indices else [boxes, scores, classes, valid]
 
     def forward_heads(self, imgs):

@@ -102,7 +102,15 @@ struct y4_engine {
     float4* d_flush = nullptr; size_t flush_elems = 0;
     ncclComm_t comm = nullptr; int rank = 0, nranks = 1;
     void* d_gather = nullptr; size_t gather_bytes = 0;
-    std::map<int, std::pair<cudaGraphExec_t, int64_t>> graphs;   // key = batch*4 + what -> (exec, kernels per replay)
+    std::map<int, std::pair<cudaGraphExec_t, int64_t>> graphs;   // key = (batch*4 + what)*2 + input slot -> (exec, kernels per replay)
+    // pipelined host path (y4_submit / y4_collect): two input buffers, H2D on its own stream, results staged in pinned memory
+    float* d_img_slot[2] = {nullptr, nullptr};
+    int img_slot = 0;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    char* stage[2] = {nullptr, nullptr};          // pinned: boxes | scores | classes | idx | valid | overflow
+    int64_t n_submitted = 0, n_collected = 0;
+    int sub_batch[2] = {0, 0};
 };
 
 namespace {
@@ -609,6 +617,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     const int S = cfg->img_size, B = cfg->max_batch, mb = cfg->max_boxes;
 #define CREATE_TRY(call) do { if ((call) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError()))); } while (0)
     CREATE_TRY(cudaMalloc(&e->d_img, sizeof(float) * 3 * S * S * B));
+    e->d_img_slot[0] = e->d_img;
     for (auto& c : e->convs) {
         CREATE_TRY(cudaMalloc(&c.d_w32, sizeof(float) * c.K * c.cout_pad));
         CREATE_TRY(cudaMalloc(&c.d_w16, sizeof(__half) * c.K * c.cout_pad));
@@ -712,7 +721,9 @@ void y4_destroy(y4_engine* e) {
     if (e->comm) nccl().CommDestroy(e->comm);
     for (auto& b : e->bufs) { cudaFree(b.ptr); cudaFree(b.ptr_lo); }
     for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_w16k32); cudaFree(c.d_w16_lo); cudaFree(c.d_wscale); cudaFree(c.d_bias); }
-    cudaFree(e->d_img);
+    cudaFree(e->d_img_slot[0]); cudaFree(e->d_img_slot[1]);
+    for (int i = 0; i < 2; i++) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); if (e->stage[i]) cudaFreeHost(e->stage[i]); }
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 3; i++) cudaFree(e->d_user_heads[i]);
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
     cudaFree(e->d_out_boxes); cudaFree(e->d_out_scores); cudaFree(e->d_out_classes);
@@ -754,6 +765,7 @@ int y4_predict(y4_engine* e, const float* imgs, int32_t batch, float* boxes, flo
                int32_t* valid, int32_t* cand_idx) {
     int rc = ready(e, batch, true); if (rc) return rc;
     if (!imgs) return fail(e, Y4_ERR_ARG, "null imgs");
+    if (e->n_submitted != e->n_collected) return fail(e, Y4_ERR_STATE, "y4_submit batches are in flight: y4_collect them first");
     const size_t n = (size_t)batch * e->cfg.img_size * e->cfg.img_size * 3;
     CUDA_TRY(e, cudaMemcpyAsync(e->d_img, imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     rc = run_forward(e, batch); if (rc) return rc;
@@ -764,6 +776,7 @@ int y4_predict(y4_engine* e, const float* imgs, int32_t batch, float* boxes, flo
 int y4_forward_heads(y4_engine* e, const float* imgs, int32_t batch, float* hs, float* hm, float* hl) {
     int rc = ready(e, batch, true); if (rc) return rc;
     if (!imgs) return fail(e, Y4_ERR_ARG, "null imgs");
+    if (e->n_submitted != e->n_collected) return fail(e, Y4_ERR_STATE, "y4_submit batches are in flight: y4_collect them first");
     const size_t n = (size_t)batch * e->cfg.img_size * e->cfg.img_size * 3;
     CUDA_TRY(e, cudaMemcpyAsync(e->d_img, imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     rc = run_forward(e, batch); if (rc) return rc;
@@ -815,7 +828,7 @@ static int run_resident_part(y4_engine* e, int batch, int what) {
         return rc;
     };
     if (!use_graph) return body();
-    const int key = batch * 4 + what;
+    const int key = (batch * 4 + what) * 2 + e->img_slot;
     auto it = e->graphs.find(key);
     if (it == e->graphs.end()) {
         const int64_t before = e->launches;
@@ -870,6 +883,79 @@ int y4_upload_heads(y4_engine* e, const float* hs, const float* hm, const float*
 int y4_fetch_results(y4_engine* e, int32_t batch, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx) {
     int rc = ready(e, batch, false); if (rc) return rc;
     return fetch(e, batch, boxes, scores, classes, valid, cand_idx);
+}
+
+// ---- pipelined host path: submit batch i+1 (async H2D on the copy stream) while batch i computes; results come back
+// through pinned staging.  Depth 2: at most two submits may be outstanding.
+static size_t stage_bytes(const y4_engine* e) {
+    const size_t mb = e->cfg.max_boxes, B = e->cfg.max_batch;
+    return B * (mb * 4 * 4 + mb * 4 * 3 + 4) + 16;
+}
+int y4_submit(y4_engine* e, const float* imgs, int32_t batch) {
+    int rc = ready(e, batch, true); if (rc) return rc;
+    if (!imgs) return fail(e, Y4_ERR_ARG, "null imgs");
+    if (e->n_submitted - e->n_collected >= 2) return fail(e, Y4_ERR_STATE, "two batches already in flight: call y4_collect first");
+    const int S = e->cfg.img_size, B = e->cfg.max_batch, mb = e->cfg.max_boxes;
+    if (!e->copy_stream) {
+        CUDA_TRY(e, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(e, cudaMalloc(&e->d_img_slot[1], sizeof(float) * 3 * S * S * B));
+        for (int i = 0; i < 2; i++) {
+            CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_h2d[i], cudaEventDisableTiming));
+            CUDA_TRY(e, cudaEventCreateWithFlags(&e->ev_done[i], cudaEventDisableTiming));
+            CUDA_TRY(e, cudaHostAlloc((void**)&e->stage[i], stage_bytes(e), cudaHostAllocDefault));
+        }
+    }
+    const int slot = (int)(e->n_submitted & 1);
+    // the slot's previous occupant (submit n-2) was collected, hence its compute (which read d_img_slot[slot]) is done
+    const size_t n = (size_t)batch * S * S * 3;
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_img_slot[slot], imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
+    CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_h2d[slot], 0));
+    e->d_img = e->d_img_slot[slot]; e->img_slot = slot;
+    rc = run_resident_part(e, batch, 3);
+    e->d_img = e->d_img_slot[0]; e->img_slot = 0;
+    if (rc) return rc;
+    char* st = e->stage[slot];
+    size_t off = 0;
+    CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_out_boxes, sizeof(float) * 4 * mb * batch, cudaMemcpyDeviceToHost, e->stream)); off += sizeof(float) * 4 * mb * B;
+    CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_out_scores, sizeof(float) * mb * batch, cudaMemcpyDeviceToHost, e->stream)); off += sizeof(float) * mb * B;
+    CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_out_classes, sizeof(float) * mb * batch, cudaMemcpyDeviceToHost, e->stream)); off += sizeof(float) * mb * B;
+    CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_out_idx, sizeof(int) * mb * batch, cudaMemcpyDeviceToHost, e->stream)); off += sizeof(int) * mb * B;
+    CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_out_valid, sizeof(int) * batch, cudaMemcpyDeviceToHost, e->stream)); off += sizeof(int) * B;
+    CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaEventRecord(e->ev_done[slot], e->stream));
+    e->sub_batch[slot] = batch;
+    e->n_submitted++;
+    return Y4_OK;
+}
+
+int y4_collect(y4_engine* e, int32_t batch, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx) {
+    if (!e) return Y4_ERR_ARG;
+    if (e->n_collected >= e->n_submitted) return fail(e, Y4_ERR_STATE, "nothing submitted");
+    const int slot = (int)(e->n_collected & 1);
+    if (batch != e->sub_batch[slot]) return fail(e, Y4_ERR_ARG, "batch differs from the submitted one");
+    cudaSetDevice(e->cfg.device);
+    CUDA_TRY(e, cudaEventSynchronize(e->ev_done[slot]));
+    e->n_collected++;
+    const size_t mb = e->cfg.max_boxes, B = e->cfg.max_batch;
+    const char* st = e->stage[slot];
+    size_t off = 0;
+    if (boxes) memcpy(boxes, st + off, sizeof(float) * 4 * mb * batch);
+    off += sizeof(float) * 4 * mb * B;
+    if (scores) memcpy(scores, st + off, sizeof(float) * mb * batch);
+    off += sizeof(float) * mb * B;
+    if (classes) memcpy(classes, st + off, sizeof(float) * mb * batch);
+    off += sizeof(float) * mb * B;
+    if (cand_idx) memcpy(cand_idx, st + off, sizeof(int) * mb * batch);
+    off += sizeof(int) * mb * B;
+    if (valid) memcpy(valid, st + off, sizeof(int) * batch);
+    off += sizeof(int) * B;
+    int overflow = 0; memcpy(&overflow, st + off, sizeof(int));
+    if (overflow) {
+        cudaMemsetAsync(e->d_overflow, 0, sizeof(int), e->stream);
+        return fail(e, Y4_ERR_CAPACITY, "more than Y4_MAX_CANDIDATES (8192) candidates above score_threshold in one image");
+    }
+    return Y4_OK;
 }
 
 int y4_sync(y4_engine* e) {
