@@ -65,6 +65,9 @@ typedef struct y4_layer_info {
     int32_t tile_n;           /* N tile of the tcgen05 kernel (0 if kernel_kind==0) */
     int64_t flops;            /* 2*MAC per image */
     char    out_name[16];     /* name of the tensor this conv materialises (r<k> when the residual add is fused) */
+    int32_t tc_mode;          /* tcgen05 plan: 1 flat (one TMA per tap), 2 strided box, 3 flat with A-patch reuse */
+    int32_t tc_epilogue;      /* 0 per-thread global stores, 1 swizzled smem slab + TMA store */
+    int32_t tc_stages, tc_group, tc_ctas_per_sm, tc_bk;   /* ring depth, k-blocks per barrier, persistent CTAs per SM, K block */
 } y4_layer_info;
 
 /* Fills *cfg with the reference defaults (config.py) at 416x416, 80 classes, max_batch 1, fp16. */

@@ -30,7 +30,8 @@ class Y4Config(C.Structure):
 
 class Y4LayerInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('idx', 'cin', 'cout', 'ksize', 'stride', 'batch_norm', 'activation',
-                                         'out_hw', 'kernel_kind', 'tile_n')] + [('flops', C.c_int64), ('out_name', C.c_char * 16)]
+                                         'out_hw', 'kernel_kind', 'tile_n')] + [('flops', C.c_int64), ('out_name', C.c_char * 16)] + \
+               [(n, C.c_int32) for n in ('tc_mode', 'tc_epilogue', 'tc_stages', 'tc_group', 'tc_ctas_per_sm', 'tc_bk')]
 
 
 EXPORTS = [
@@ -195,7 +196,12 @@ class Engine:
         self._inflight = getattr(self, '_inflight', []) + [imgs]
 
     def collect(self, with_indices=False):
-        imgs = self._inflight.pop(0)
+        inflight = getattr(self, '_inflight', [])
+        if not inflight:                      # nothing submitted: let the engine report it (Y4_ERR_ARG -> Y4Error)
+            boxes, scores, classes, valid, idx = self._alloc_out(1)
+            self._chk(self._lib.y4_collect(self._h, 1, _ptr(boxes), _ptr(scores), _ptr(classes), _ptr(valid), _ptr(idx)))
+            raise Y4Error('collect() without a matching submit()')
+        imgs = inflight.pop(0)
         b = imgs.shape[0]
         boxes, scores, classes, valid, idx = self._alloc_out(b)
         self._chk(self._lib.y4_collect(self._h, b, _ptr(boxes), _ptr(scores), _ptr(classes), _ptr(valid), _ptr(idx)))

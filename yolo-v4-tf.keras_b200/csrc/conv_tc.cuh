@@ -41,6 +41,7 @@ struct TcParams {
     CUtensorMap tmW;
     CUtensorMap tmA_lo[4];       // split precision: low-order planes
     CUtensorMap tmW_lo;
+    CUtensorMap tmOut;           // epi = 1: output slice as [rows][cout] fp16, box {epi_cols, 32 rows} (TMA store of the epilogue slabs)
     const float* bias;
     const float* wscale;         // per-cout 1/scale of the (power-of-two scaled) split weights, nullptr -> 1
     void* out;
@@ -57,6 +58,9 @@ struct TcParams {
     // mode 3 (3x3 stride 1, A-patch reuse): one (128 + 2*Wp + 2)-row patch per 64-channel block feeds all 9 taps
     int patch_boxes, patch_bytes, patch_slots, base_off_mode;
     int mode;                    // 1 flat, 2 box
+    int epi;                     // 0: per-thread global stores; 1: swizzled smem slab per warp -> TMA store (flat modes, fp16 out)
+    int epi_cols;                // channels per slab row: 64 (128 B rows, SWIZZLE_128B) or 32 (64 B rows, SWIZZLE_64B)
+    long long rows_alloc;        // max_batch * Hp * Wp: rows that exist in the output / skip buffers
     // flat
     int Hp, Wp;                  // padded dims (same for in and out)
     long long M_total;           // batch * Hp * Wp
@@ -118,6 +122,27 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+        ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {      // src_bytes 0 -> zero fill
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -217,6 +242,37 @@ __device__ __forceinline__ float act_tc(float x) {
     return x;
 }
 
+// Throughput-mode epilogue math (fp16 outputs).  FP32 FFMA/FMUL issue at one warp instruction per two cycles per
+// scheduler and MUFU at one per eight, so the op count per element is what bounds the 1x1 layers at 304^2/152^2.
+// mish with the log2(e) factor folded into the bias (b2 = b * log2 e, staged in smem):
+//   u = acc * log2e + b2 = x * log2e;  t = 2^u = e^x;  tanh(softplus(x)) = 1 - 2 / ((t + 1)^2 + 1)
+//   mish = x * (...) = u * (ln2 - 2 ln2 / ((t + 1)^2 + 1))            5 FMA-pipe ops + 1 FMNMX + 2 MUFU
+// (the subtraction loses relative accuracy only where |mish| < 1e-3; absolute error stays below 2e-6)
+template <int ACT>
+__device__ __forceinline__ float act_fast(float acc, float b) {
+    if (ACT == 2) {
+        const float u = fmaf(acc, 1.4426950408889634f, b);
+        const float t = ex2_approx(fminf(u, 29.f));
+        const float a = t + 1.f;
+        const float g = fmaf(rcp_approx(fmaf(a, a, 1.f)), -1.3862943611198906f, 0.6931471805599453f);
+        return u * g;
+    }
+    const float x = acc + b;
+    if (ACT == 1) return fmaxf(x, 0.1f * x);
+    return x;
+}
+template <int ACT>
+__device__ __forceinline__ void act32_fast(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+        const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
+        f[j + 0] = act_fast<ACT>(__uint_as_float(v[j + 0]), b4.x);
+        f[j + 1] = act_fast<ACT>(__uint_as_float(v[j + 1]), b4.y);
+        f[j + 2] = act_fast<ACT>(__uint_as_float(v[j + 2]), b4.z);
+        f[j + 3] = act_fast<ACT>(__uint_as_float(v[j + 3]), b4.w);
+    }
+}
+
 template <int ACT>
 __device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], const float* __restrict__ bias, const float* __restrict__ scale, float (&f)[32]) {
 #pragma unroll
@@ -296,9 +352,15 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
             for (int j = 0; j < 4; j++) rlo[j] = __ldg(rq + j);
         }
     }
-    if (p.act == 2) bias_act32<2>(v, sbias + col0, sscale + col0, f);
-    else if (p.act == 1) bias_act32<1>(v, sbias + col0, sscale + col0, f);
-    else bias_act32<0>(v, sbias + col0, sscale + col0, f);
+    if (SPLIT) {
+        if (p.act == 2) bias_act32<2>(v, sbias + col0, sscale + col0, f);
+        else if (p.act == 1) bias_act32<1>(v, sbias + col0, sscale + col0, f);
+        else bias_act32<0>(v, sbias + col0, sscale + col0, f);
+    } else {                                                // sbias holds b * log2(e) for mish layers (see act_fast)
+        if (p.act == 2) act32_fast<2>(v, sbias + col0, f);
+        else if (p.act == 1) act32_fast<1>(v, sbias + col0, f);
+        else act32_fast<0>(v, sbias + col0, f);
+    }
     if (p.res) {
         if (SPLIT) {
             float rs[32];
@@ -341,6 +403,71 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
     }
 }
 
+// ---- epi = 1: slab epilogue ---------------------------------------------------------------------------------------
+// Per-thread global stores put 32 different 128 B lines behind every STG/LDG (one L1 wavefront each): on the
+// HBM-bound layers the L1 wavefront queue, not DRAM, was the limit.  Here each epilogue warp owns two slabs of
+// 32 rows x (epi_cols * 2) bytes in the TMA swizzle (16 B chunk index ^ row bits; slabs are 1024 B aligned, so the row
+// bits are the address bits the hardware uses).  A thread writes its own accumulator row into the slab (conflict free:
+// the 8 lanes of an st.shared.v4 phase land in 8 different chunks), one lane issues a TMA store of the whole box, and
+// the skip tensor, when there is one, is brought into the slab beforehand by coalesced cp.async (8 lanes per row).
+// Halo rows are stored as zeros (they are zero anyway), which is what lets a plain box store replace the row mask.
+constexpr uint32_t kSlabBytes = 4096;
+constexpr uint32_t kEpiBytes = 4u * 2u * kSlabBytes;          // 4 epilogue warps x 2 slabs
+
+__device__ __forceinline__ uint32_t slab_chunk_addr(uint32_t slab, int row, int chunk, bool cols64) {
+    return cols64 ? slab + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4)
+                  : slab + (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
+}
+
+// skip-tile rows [row0, row0 + 32) x channels [col0, col0 + epi_cols) -> slab (rows past the buffer: zero fill)
+__device__ __forceinline__ void res_prefetch(const TcParams& p, uint32_t slab, long long row0, int col0, int lane, bool cols64) {
+    const int cpr = cols64 ? 8 : 4;                          // 16 B chunks per row
+    const int rpi = 32 / cpr;                                // rows per instruction
+    const int ch = lane % cpr, rsub = lane / cpr;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        if (i < cpr) {
+            const int row = i * rpi + rsub;
+            const long long gr = row0 + row;
+            const bool ok = gr < p.rows_alloc;
+            const __half* src = p.res + (ok ? gr : 0ll) * p.res_ld + p.res_choff + col0 + ch * 8;
+            cp_async16(slab_chunk_addr(slab, row, ch, cols64), src, ok ? 16 : 0);
+        }
+    }
+    cp_async_commit();
+}
+
+// 32 accumulator columns of this thread's row -> activation (-> + skip chunk from the slab) -> fp16 -> slab chunks 4h..4h+3
+__device__ __forceinline__ void epi_half(const TcParams& p, const uint32_t (&v)[32], const float* sb, uint32_t slab, int lane, int h,
+                                         bool interior, bool has_res, bool cols64) {
+    float f[32];
+    if (p.act == 2) act32_fast<2>(v, sb, f);
+    else if (p.act == 1) act32_fast<1>(v, sb, f);
+    else act32_fast<0>(v, sb, f);
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const uint32_t addr = slab_chunk_addr(slab, lane, 4 * h + j, cols64);
+        if (has_res) {
+            const uint4 r = lds128(addr);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&r);
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+                const float2 x = __half22float2(h2[t]);
+                f[j * 8 + t * 2] += x.x; f[j * 8 + t * 2 + 1] += x.y;
+            }
+        }
+        uint4 o;
+        __half2 h0 = __floats2half2_rn(f[8 * j + 0], f[8 * j + 1]);
+        __half2 h1 = __floats2half2_rn(f[8 * j + 2], f[8 * j + 3]);
+        __half2 h2o = __floats2half2_rn(f[8 * j + 4], f[8 * j + 5]);
+        __half2 h3 = __floats2half2_rn(f[8 * j + 6], f[8 * j + 7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2o); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        if (!interior) o = make_uint4(0u, 0u, 0u, 0u);
+        sts128(addr, o);
+    }
+}
+
 template <int BN, int BK, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int SWZ = BK * 2;
@@ -361,11 +488,13 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     // then: full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), pfull[4], pempty[4], bias[bias_n]
     const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : (uint32_t)(S * G) * SBYTES;
     const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);      // mode 3: first B stage
-    const uint32_t bars = base + ring_bytes;
+    const uint32_t epi_bytes = (!SPLIT && p.epi) ? kEpiBytes : 0u;   // epilogue slabs (1024 B aligned: ring_bytes is a multiple of 1024)
+    const uint32_t slabs = base + ring_bytes;
+    const uint32_t bars = slabs + epi_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
     const uint32_t tmem_slot = bars + 16u * S + 32u;
     const uint32_t bar_pfull = bars + 16u * S + 48u, bar_pempty = bars + 16u * S + 80u;
-    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + 16u * S + 112u);
+    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + epi_bytes + 16u * S + 112u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* dbg = (p.dbg && blockIdx.x < 4096) ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
@@ -380,11 +509,14 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 4); }
         for (int a = 0; a < 4; a++) { mbar_init(bar_pfull + 8u * a, 1); mbar_init(bar_pempty + 8u * a, 1); }
         if (p.mode == 3) tma_prefetch_desc(&p.tmA[1]);
+        if (p.epi) tma_prefetch_desc(&p.tmOut);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     float* sscale = sbias + p.bias_n;
-    if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 128) { sbias[i] = p.bias[i]; sscale[i] = p.wscale ? p.wscale[i] : 1.0f; }
+    // non-split mish layers keep b * log2(e) (act_fast)
+    const float bmul = (!SPLIT && p.act == 2) ? 1.4426950408889634f : 1.0f;
+    if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 128) { sbias[i] = p.bias[i] * bmul; sscale[i] = p.wscale ? p.wscale[i] : 1.0f; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -449,8 +581,13 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES) * (SPLIT ? 2u : 1u));
                     for (int kk = 0; kk < gcount; kk++) {
                         const int kb = kb0 + kk;
-                        const int tap = kb / p.kb_per_tap;
-                        const int c0 = (kb - tap * p.kb_per_tap) * BK;
+                        // K order.  flat 3x3: channel block outer, tap inner -- the order the A-patch mode (3) needs, so both
+                        // modes accumulate identically and the autotuner may pick either.  box: tap outer.
+                        int tap, cb;
+                        if (p.mode == 1 && p.ksize == 3) { cb = kb / 9; tap = kb - cb * 9; }
+                        else { tap = kb / p.kb_per_tap; cb = kb - tap * p.kb_per_tap; }
+                        const int c0 = cb * BK;
+                        const int wcol = (tap * p.kb_per_tap + cb) * BK;
                         const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * SBYTES;
                         if (p.mode == 1) {
                             int shift = 0;
@@ -460,7 +597,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                             const int kh = tap / 3, kw = tap - kh * 3;
                             tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
                         }
-                        tma_load_2d(sa + A_BYTES, &p.tmW, fb, kb * BK, tc.n0);
+                        tma_load_2d(sa + A_BYTES, &p.tmW, fb, wcol, tc.n0);
                         if (SPLIT) {
                             const uint32_t sl = sa + STAGE_BYTES;
                             if (p.mode == 1) {
@@ -471,7 +608,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                                 const int kh = tap / 3, kw = tap - kh * 3;
                                 tma_load_4d(sl, &p.tmA_lo[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
                             }
-                            tma_load_2d(sl + A_BYTES, &p.tmW_lo, fb, kb * BK, tc.n0);
+                            tma_load_2d(sl + A_BYTES, &p.tmW_lo, fb, wcol, tc.n0);
                         }
                     }
                     if (it == 0) Y4_STAMP(2);
@@ -553,7 +690,11 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
         const int q = warp & 3;
         const int r = q * 32 + lane;                        // row of the tile
-        uint32_t ti = 0;
+        uint32_t ti = 0, sit = 0;                           // sit: slab groups issued by this warp (epi = 1)
+        if (!SPLIT && p.epi && p.res && (int)blockIdx.x < p.num_tiles) {
+            const TileCoord t0 = decode_tile<BN>(p, (int)blockIdx.x);
+            res_prefetch(p, slabs + (uint32_t)q * 2u * kSlabBytes, t0.m0 + q * 32, t0.n0, lane, p.epi_cols == 64);
+        }
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
             const TileCoord tc = decode_tile<BN>(p, tile);
             const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
@@ -582,6 +723,41 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN;
             uint32_t va[32], vb[32];
             tmem_ld32_issue(tacc, va);
+            if (!SPLIT && p.epi) {
+                const bool cols64 = p.epi_cols == 64;
+                const bool has_res = p.res != nullptr;
+                const uint32_t my_slabs = slabs + (uint32_t)q * 2u * kSlabBytes;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 64, sit++) {
+                    const uint32_t slab = my_slabs + (sit & 1u) * kSlabBytes;
+                    if (has_res) { cp_async_wait_all(); __syncwarp(); }      // this group's skip tile is in the slab
+                    tmem_ld_wait(va);
+                    tmem_ld32_issue(tacc + (uint32_t)(c0 + 32), vb);
+                    epi_half(p, va, sbias + tc.n0 + c0, slab, lane, 0, valid, has_res, cols64);
+                    __syncwarp();
+                    tmem_ld_wait(vb);
+                    if (c0 + 64 < BN) tmem_ld32_issue(tacc + (uint32_t)(c0 + 64), va);
+                    else { tc_fence_before(); if (lane == 0) mbar_arrive(bar_tempty + 8u * as); }   // accumulator stage drained
+                    if (cols64) epi_half(p, vb, sbias + tc.n0 + c0 + 32, slab, lane, 1, valid, has_res, cols64);
+                    // the previous group's store has had a whole group of math to read its slab: free it, refill it with
+                    // the next group's skip tile, then hand this slab to the TMA
+                    if (lane == 0) bulk_wait_read<0>();
+                    __syncwarp();
+                    if (has_res) {
+                        int nc0 = c0 + 64, ntile = tile;
+                        if (nc0 >= BN) { nc0 = 0; ntile = tile + (int)gridDim.x; }
+                        if (ntile < p.num_tiles) {
+                            const TileCoord tn = decode_tile<BN>(p, ntile);
+                            res_prefetch(p, my_slabs + ((sit + 1u) & 1u) * kSlabBytes, tn.m0 + q * 32, tn.n0 + nc0, lane, cols64);
+                        }
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&p.tmOut, slab, tc.n0 + c0, (int)(tc.m0 + q * 32)); bulk_commit(); }
+                }
+                if (ti == 0 && threadIdx.x == 64) Y4_STAMP(7);
+                continue;
+            }
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 64) {
                 tmem_ld_wait(va);
@@ -598,6 +774,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             if (lane == 0) mbar_arrive(bar_tempty + 8u * as);
             if (ti == 0 && threadIdx.x == 64) Y4_STAMP(7);
         }
+        if (!SPLIT && p.epi && lane == 0) bulk_wait_all();  // the slabs must outlive the TMA reads, the writes the kernel
     }
     tc_fence_before();
     __syncthreads();
@@ -687,7 +864,7 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 }
 
 // returns kernel kind (0 = not eligible -> CUDA-core kernel, 1 = flat GEMM, 2 = strided box), <0 on error
-inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0, int group = 1) {
+inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0, int group = 1, int epi = 0) {
     if (d.raw_in) return 0;                                   // conv 0 (cin = 3): CUDA-core kernel
     const int bk = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 0);
     if (!bk) return 0;
@@ -761,6 +938,21 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
                 }
             }
     }
+    size_t epi_bytes = 0;
+    if (epi) {
+        // slab epilogue: flat tiles, fp16 output written in place (no upsample), whole 64-channel groups (or one of 32)
+        if (P.kind != 1 || d.out_f32 || d.upsample || d.split || !(p.cout_store % 64 == 0 || (p.cout_store == 32 && bn == 64))) return 0;
+        p.epi = 1;
+        p.epi_cols = p.cout_store % 64 == 0 ? 64 : 32;
+        p.rows_alloc = (long long)d.max_batch * in_Hp * in_Wp;
+        cuuint64_t dims[2] = {(cuuint64_t)p.cout_store, (cuuint64_t)p.rows_alloc};
+        cuuint64_t str[1] = {(cuuint64_t)d.out_ld * 2};
+        cuuint32_t box[2] = {(cuuint32_t)p.epi_cols, 32};
+        char* out_base = reinterpret_cast<char*>(d.out) + (size_t)d.out_choff * 2;
+        if (!encode_map(&p.tmOut, out_base, 2, dims, str, box, p.epi_cols * 2, err)) return -1;
+        epi_bytes = kEpiBytes;
+        if ((size_t)smem_budget_kb * 1024 <= epi_bytes + 16 * 1024) return 0;
+    }
     size_t stage_bytes = ((size_t)128 * bk * 2 + (size_t)bn * bk * 2) * (d.split ? 2 : 1);
     size_t ring_fixed = 0;
     if (!patch && getenv("Y4_FORCE_PATCH") && P.kind == 1 && d.k == 3 && bk == 64) { patch = 1; if (smem_budget_kb < 200) smem_budget_kb = 200; }
@@ -781,13 +973,13 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
         if (!encode_map(&p.tmA[1], in_base, 2, dims, str, box, swz, err)) return -1;
         ring_fixed = (size_t)p.patch_slots * p.patch_bytes;
         stage_bytes = (size_t)bn * bk * 2;                            // the ring holds B tiles only
-        if ((size_t)smem_budget_kb * 1024 < ring_fixed + 2 * stage_bytes) return 0;
+        if ((size_t)smem_budget_kb * 1024 < ring_fixed + 2 * stage_bytes + epi_bytes) return 0;
     }
     if (patch || group < 1) group = 1;
     if (group > p.num_kb) group = p.num_kb;
     p.group = group;
     stage_bytes *= (size_t)group;
-    int S = (int)(((size_t)smem_budget_kb * 1024 - ring_fixed) / stage_bytes);   // default budget ~100 KB: two CTAs share an SM
+    int S = (int)(((size_t)smem_budget_kb * 1024 - ring_fixed - epi_bytes) / stage_bytes);   // default budget ~100 KB: two CTAs share an SM
     if (S < 2) { if (group > 1) return 0; S = 2; }
     if (S > 8) S = 8;
     const int max_useful = patch ? 9 * p.kb_per_tap : (p.num_kb + group - 1) / group;
@@ -797,7 +989,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     P.stages = S; p.stages = S;
     p.n_tiles = (p.cout_store + bn - 1) / bn;
     p.bias_n = d.cout_pad;
-    P.smem = 1024 + ring_fixed + S * stage_bytes + 16 * S + 112 + 8 * (size_t)p.bias_n;   // bias + weight-scale arrays
+    P.smem = 1024 + ring_fixed + S * stage_bytes + epi_bytes + 16 * S + 112 + 8 * (size_t)p.bias_n;   // bias + weight-scale arrays
     if (P.smem > 220 * 1024) { *err = "smem budget exceeded"; return -1; }
     int cps = (int)((227 * 1024) / (P.smem + 1024));            // +1 KB: per-CTA reserved shared memory
     const int tmem_cols = 2 * bn;

@@ -676,32 +676,37 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             // order, so every candidate produces bit-identical outputs.  Time each on the (still zero) buffers.
             const char* at = getenv("Y4_AUTOTUNE");
             if (kind > 0 && !(at && at[0] == '0')) {
-                // {N tile, smem budget KB}: budget sets the ring depth and whether one or two persistent CTAs share an SM
-                // {N tile, smem budget KB, A-patch reuse, k-blocks per stage}
+                // {N tile, smem budget KB, A-patch reuse, k-blocks per stage}: the budget sets the ring depth and whether one or
+                // two persistent CTAs share an SM.  Each is tried with both epilogues (per-thread stores / slab + TMA store).
+                // Every candidate accumulates K in the same order and rounds once, so outputs are bit-identical across them.
                 const int cand[][4] = {{64, 99, 0, 1}, {64, 200, 0, 1}, {128, 99, 0, 1}, {128, 150, 0, 1}, {128, 200, 0, 1},
                                        {256, 150, 0, 1}, {256, 200, 0, 1},
                                        {64, 99, 0, 2}, {64, 205, 0, 3}, {64, 205, 0, 99}, {128, 205, 0, 2}, {128, 205, 0, 3},
                                        {128, 205, 0, 99}, {256, 205, 0, 2},
-                                       {64, 205, 1, 1}, {128, 205, 1, 1}, {256, 205, 1, 1}};     // last three: A-patch reuse
+                                       {64, 205, 1, 1}, {128, 205, 1, 1}, {256, 205, 1, 1}, {128, 110, 1, 1}};     // last four: A-patch reuse
                 float best_ms = 1e30f;
                 TcConvPlan best = c.tc;
-                // A-patch reuse sums K in a different order (channel-block outer, tap inner), so unlike the tile
-                // candidates it is NOT bit-identical to mode 1; it is opt-in (Y4_PATCH=1) to keep results independent
-                // of what the autotuner picks on a given GPU / batch size (multi-GPU gathers are compared bitwise).
-                static const bool allow_patch = getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '1';
-                for (auto& cd : cand) {
-                    if (cd[2] && !allow_patch) continue;
-                    TcConvPlan trial;
-                    std::string er2;
-                    if (tc_plan(d, &trial, &er2, cd[0], cd[1], cd[2], cd[3]) != kind) continue;
-                    if (tc_launch(trial, B, e->stream) != 0) { cudaGetLastError(); continue; }      // warm-up + smem attribute
-                    cudaEventRecord(e->ev0, e->stream);
-                    for (int rep = 0; rep < 3; rep++) tc_launch(trial, B, e->stream);
-                    cudaEventRecord(e->ev1, e->stream);
-                    if (cudaEventSynchronize(e->ev1) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, "autotune launch failed for conv " + std::to_string(c.idx)));
-                    float ms = 0.f;
-                    cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-                    if (ms < best_ms) { best_ms = ms; best = trial; }
+                static const bool allow_patch = !(getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '0');
+                static const int epi_mode = getenv("Y4_EPI") ? atoi(getenv("Y4_EPI")) : 1;     // 0 never, 1 autotune, 2 wherever eligible
+                bool have_epi = false;
+                for (int epi = 1; epi >= 0; epi--) {
+                    if (epi && epi_mode == 0) continue;
+                    if (!epi && epi_mode == 2 && have_epi) continue;
+                    for (auto& cd : cand) {
+                        if (cd[2] && !allow_patch) continue;
+                        TcConvPlan trial;
+                        std::string er2;
+                        if (tc_plan(d, &trial, &er2, cd[0], cd[1], cd[2], cd[3], epi) != kind) continue;
+                        if (tc_launch(trial, B, e->stream) != 0) { cudaGetLastError(); continue; }      // warm-up + smem attribute
+                        cudaEventRecord(e->ev0, e->stream);
+                        for (int rep = 0; rep < 3; rep++) tc_launch(trial, B, e->stream);
+                        cudaEventRecord(e->ev1, e->stream);
+                        if (cudaEventSynchronize(e->ev1) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, "autotune launch failed for conv " + std::to_string(c.idx)));
+                        float ms = 0.f;
+                        cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+                        if (epi) have_epi = true;
+                        if (ms < best_ms) { best_ms = ms; best = trial; }
+                    }
                 }
                 c.tc = best;
             }
@@ -1015,6 +1020,9 @@ int y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info) {
     info->tile_n = c.kind ? c.tc.tile_n : 0;
     info->flops = 2ll * c.N_OH * c.N_OH * c.cout * c.K;
     snprintf(info->out_name, sizeof(info->out_name), "%s", c.out_name.c_str());
+    const bool tc = c.kind == 1 || c.kind == 2;
+    info->tc_mode = tc ? c.tc.p.mode : 0; info->tc_epilogue = tc ? c.tc.p.epi : 0; info->tc_stages = tc ? c.tc.stages : 0;
+    info->tc_group = tc ? c.tc.p.group : 0; info->tc_ctas_per_sm = tc ? c.tc.ctas_per_sm : 0; info->tc_bk = tc ? c.tc.bk : 0;
     return Y4_OK;
 }
 
