@@ -66,8 +66,10 @@ typedef struct y4_layer_info {
     int64_t flops;            /* 2*MAC per image */
     char    out_name[16];     /* name of the tensor this conv materialises (r<k> when the residual add is fused) */
     int32_t tc_mode;          /* tcgen05 plan: 1 flat (one TMA per tap), 2 strided box, 3 flat with A-patch reuse */
-    int32_t tc_epilogue;      /* 0 per-thread global stores, 1 swizzled smem slab + TMA store */
+    int32_t tc_epilogue;      /* 0 per-thread global stores; 32 / 64: swizzled smem slab + TMA store in groups of that many channels */
     int32_t tc_stages, tc_group, tc_ctas_per_sm, tc_bk;   /* ring depth, k-blocks per barrier, persistent CTAs per SM, K block */
+    int32_t tc_epi_warps;     /* 4 or 8 epilogue warps */
+    int32_t tc_resident_w;    /* 1: the weight matrix stays in shared memory for the life of the CTA */
 } y4_layer_info;
 
 /* Fills *cfg with the reference defaults (config.py) at 416x416, 80 classes, max_batch 1, fp16. */

@@ -29,7 +29,7 @@ for i, t in enumerate(ms):
     l = layers[li]; li += 1
     gf = l['flops'] * batch / 1e9
     rows.append({'name': f"c{l['idx']}", 'cin': l['cin'], 'cout': l['cout'], 'k': l['ksize'], 's': l['stride'], 'hw': l['out_hw'],
-                 'kind': l['kernel_kind'], 'bn': l['tile_n'], 'mode': l['tc_mode'], 'epi': l['tc_epilogue'], 'st': l['tc_stages'], 'grp': l['tc_group'], 'cps': l['tc_ctas_per_sm'], 'ms': float(t), 'gflop': float(gf), 'tflops': float(gf / t) if t > 0 else 0.0})
+                 'kind': l['kernel_kind'], 'bn': l['tile_n'], 'mode': l['tc_mode'], 'epi': l['tc_epilogue'], 'st': l['tc_stages'], 'grp': l['tc_group'], 'cps': l['tc_ctas_per_sm'], 'nepi': l['tc_epi_warps'], 'bres': l['tc_resident_w'], 'ms': float(t), 'gflop': float(gf), 'tflops': float(gf / t) if t > 0 else 0.0})
 tot = float(ms.sum())
 out = {'size': size, 'batch': batch, 'total_ms': tot, 'img_per_s': float(batch / tot * 1e3), 'layers': rows}
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)

@@ -31,7 +31,7 @@ class Y4Config(C.Structure):
 class Y4LayerInfo(C.Structure):
     _fields_ = [(n, C.c_int32) for n in ('idx', 'cin', 'cout', 'ksize', 'stride', 'batch_norm', 'activation',
                                          'out_hw', 'kernel_kind', 'tile_n')] + [('flops', C.c_int64), ('out_name', C.c_char * 16)] + \
-               [(n, C.c_int32) for n in ('tc_mode', 'tc_epilogue', 'tc_stages', 'tc_group', 'tc_ctas_per_sm', 'tc_bk')]
+               [(n, C.c_int32) for n in ('tc_mode', 'tc_epilogue', 'tc_stages', 'tc_group', 'tc_ctas_per_sm', 'tc_bk', 'tc_epi_warps', 'tc_resident_w')]
 
 
 EXPORTS = [

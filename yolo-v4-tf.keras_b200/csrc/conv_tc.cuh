@@ -41,7 +41,7 @@ struct TcParams {
     CUtensorMap tmW;
     CUtensorMap tmA_lo[4];       // split precision: low-order planes
     CUtensorMap tmW_lo;
-    CUtensorMap tmOut;           // epi = 1: output slice as [rows][cout] fp16, box {epi_cols, 32 rows} (TMA store of the epilogue slabs)
+    CUtensorMap tmOut;           // epi = 1: output slice as [rows][cout] fp16, box {32 channels, 32 rows}, SWIZZLE_64B (TMA store of the slabs)
     const float* bias;
     const float* wscale;         // per-cout 1/scale of the (power-of-two scaled) split weights, nullptr -> 1
     void* out;
@@ -59,7 +59,8 @@ struct TcParams {
     int patch_boxes, patch_bytes, patch_slots, base_off_mode;
     int mode;                    // 1 flat, 2 box
     int epi;                     // 0: per-thread global stores; 1: swizzled smem slab per warp -> TMA store (flat modes, fp16 out)
-    int epi_cols;                // channels per slab row: 64 (128 B rows, SWIZZLE_128B) or 32 (64 B rows, SWIZZLE_64B)
+    int bres;                    // 1: the whole weight matrix is loaded once per CTA and stays in shared memory (n_tiles == 1)
+    int epi_gw;                  // slab group width in channels: 32 (64 B rows, SWIZZLE_64B) or 64 (128 B rows, SWIZZLE_128B; 4 epilogue warps only)
     long long rows_alloc;        // max_batch * Hp * Wp: rows that exist in the output / skip buffers
     // flat
     int Hp, Wp;                  // padded dims (same for in and out)
@@ -72,7 +73,7 @@ struct TcParams {
 struct TcConvPlan {
     TcParams p;
     int kind = 0;                // 1 flat, 2 box
-    int tile_n = 0, bk = 64, stages = 0, ctas_per_sm = 1;
+    int tile_n = 0, bk = 64, stages = 0, ctas_per_sm = 1, nepi = 4;
     size_t smem = 0;
     int in_Hp = 0, in_Wp = 0;
 };
@@ -286,7 +287,6 @@ __device__ __forceinline__ void bias_act32(const uint32_t (&v)[32], const float*
     }
 }
 
-constexpr int kTcThreads = 192;
 
 struct TileCoord { long long m0; int img, oh0, ow0, n0; };
 
@@ -404,24 +404,24 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
 }
 
 // ---- epi = 1: slab epilogue ---------------------------------------------------------------------------------------
-// Per-thread global stores put 32 different 128 B lines behind every STG/LDG (one L1 wavefront each): on the
-// HBM-bound layers the L1 wavefront queue, not DRAM, was the limit.  Here each epilogue warp owns two slabs of
-// 32 rows x (epi_cols * 2) bytes in the TMA swizzle (16 B chunk index ^ row bits; slabs are 1024 B aligned, so the row
-// bits are the address bits the hardware uses).  A thread writes its own accumulator row into the slab (conflict free:
-// the 8 lanes of an st.shared.v4 phase land in 8 different chunks), one lane issues a TMA store of the whole box, and
-// the skip tensor, when there is one, is brought into the slab beforehand by coalesced cp.async (8 lanes per row).
+// Per-thread global stores put 32 different 128 B lines behind every STG/LDG (one L1 wavefront each).  Here each
+// epilogue warp owns two slabs of 32 rows x 32 channels (64 B rows) in the TMA SWIZZLE_64B layout (16 B chunk index ^
+// address bits [7,9); slabs are 1024 B aligned).  A thread writes its own accumulator row into the slab (conflict free:
+// the 8 lanes of an st.shared.v4 phase land in 8 different bank groups), one lane issues a TMA store of the box, and the
+// skip tensor, when there is one, is brought into the slab beforehand by coalesced cp.async (4 lanes per row).
 // Halo rows are stored as zeros (they are zero anyway), which is what lets a plain box store replace the row mask.
-constexpr uint32_t kSlabBytes = 4096;
-constexpr uint32_t kEpiBytes = 4u * 2u * kSlabBytes;          // 4 epilogue warps x 2 slabs
+// With NEPI = 8 two warps share each TMEM lane quarter and take alternate 32-column groups.
+constexpr uint32_t kSlabBytes = 2048;                         // 32 rows x 32 channels; a 64-channel group uses two
+__host__ __device__ constexpr uint32_t epi_slab_bytes(int nepi, int gw) { return (uint32_t)nepi * 2u * kSlabBytes * (uint32_t)(gw / 32); }
 
-__device__ __forceinline__ uint32_t slab_chunk_addr(uint32_t slab, int row, int chunk, bool cols64) {
-    return cols64 ? slab + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4)
-                  : slab + (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
+__device__ __forceinline__ uint32_t slab_chunk_addr(uint32_t slab, int row, int chunk, bool gw64) {
+    return gw64 ? slab + (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4)
+                : slab + (uint32_t)row * 64u + (uint32_t)((chunk ^ ((row >> 1) & 3)) << 4);
 }
 
-// skip-tile rows [row0, row0 + 32) x channels [col0, col0 + epi_cols) -> slab (rows past the buffer: zero fill)
-__device__ __forceinline__ void res_prefetch(const TcParams& p, uint32_t slab, long long row0, int col0, int lane, bool cols64) {
-    const int cpr = cols64 ? 8 : 4;                          // 16 B chunks per row
+// skip-tile rows [row0, row0 + 32) x channels [col0, col0 + 32|64) -> slab (rows past the buffer: zero fill)
+__device__ __forceinline__ void res_prefetch(const TcParams& p, uint32_t slab, long long row0, int col0, int lane, bool gw64) {
+    const int cpr = gw64 ? 8 : 4;                            // 16 B chunks per row
     const int rpi = 32 / cpr;                                // rows per instruction
     const int ch = lane % cpr, rsub = lane / cpr;
 #pragma unroll
@@ -431,22 +431,22 @@ __device__ __forceinline__ void res_prefetch(const TcParams& p, uint32_t slab, l
             const long long gr = row0 + row;
             const bool ok = gr < p.rows_alloc;
             const __half* src = p.res + (ok ? gr : 0ll) * p.res_ld + p.res_choff + col0 + ch * 8;
-            cp_async16(slab_chunk_addr(slab, row, ch, cols64), src, ok ? 16 : 0);
+            cp_async16(slab_chunk_addr(slab, row, ch, gw64), src, ok ? 16 : 0);
         }
     }
     cp_async_commit();
 }
 
 // 32 accumulator columns of this thread's row -> activation (-> + skip chunk from the slab) -> fp16 -> slab chunks 4h..4h+3
-__device__ __forceinline__ void epi_half(const TcParams& p, const uint32_t (&v)[32], const float* sb, uint32_t slab, int lane, int h,
-                                         bool interior, bool has_res, bool cols64) {
+__device__ __forceinline__ void epi_group(const TcParams& p, const uint32_t (&v)[32], const float* sb, uint32_t slab, int lane, int h,
+                                          bool interior, bool has_res, bool gw64) {
     float f[32];
     if (p.act == 2) act32_fast<2>(v, sb, f);
     else if (p.act == 1) act32_fast<1>(v, sb, f);
     else act32_fast<0>(v, sb, f);
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const uint32_t addr = slab_chunk_addr(slab, lane, 4 * h + j, cols64);
+        const uint32_t addr = slab_chunk_addr(slab, lane, 4 * h + j, gw64);
         if (has_res) {
             const uint4 r = lds128(addr);
             const __half2* h2 = reinterpret_cast<const __half2*>(&r);
@@ -468,8 +468,14 @@ __device__ __forceinline__ void epi_half(const TcParams& p, const uint32_t (&v)[
     }
 }
 
-template <int BN, int BK, bool SPLIT>
-__global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_constant__ TcParams p) {
+// Programmatic dependent launch: the next layer's CTAs may start (prologue only) while this grid drains; they block in
+// pdl_wait() until this grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <int BN, int BK, bool SPLIT, int NEPI>
+__global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : 2) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    static_assert(NEPI == 4 || (NEPI == 8 && !SPLIT), "8 epilogue warps: slab epilogue only");
     constexpr int SWZ = BK * 2;
     constexpr int A_BYTES = 128 * BK * 2;
     constexpr int B_BYTES = BN * BK * 2;
@@ -484,21 +490,27 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     const int S = p.stages;
     const int G = p.group;                                  // k-blocks per stage (modes 1,2)
     const uint32_t SBYTES = SPLIT ? 2u * STAGE_BYTES : (uint32_t)STAGE_BYTES;   // split: [A_hi|B_hi|A_lo|B_lo]
-    // modes 1,2: S stages of G x (A | B).   mode 3: patch_slots patches, then S stages of B only.
-    // then: full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), pfull[4], pempty[4], bias[bias_n]
-    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : (uint32_t)(S * G) * SBYTES;
+    // modes 1,2: [resident W: num_kb x B, when p.bres] then S stages of G x (A | B) (A only when p.bres).
+    // mode 3: patch_slots patches, then S stages of B only.
+    // then: epilogue slabs, full[S], empty[S], tfull[2], tempty[2], tmem slot (16 B), pfull[4], pempty[4], bias[bias_n]
+    const uint32_t wres_bytes = p.bres ? (uint32_t)p.num_kb * (uint32_t)B_BYTES : 0u;
+    const uint32_t ASTRIDE = p.bres ? (uint32_t)A_BYTES : SBYTES;                 // bytes per k-block slot of the ring
+    const uint32_t ring0 = base + wres_bytes;                                       // first ring stage (modes 1,2)
+    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : wres_bytes + (uint32_t)(S * G) * ASTRIDE;
     const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);      // mode 3: first B stage
-    const uint32_t epi_bytes = (!SPLIT && p.epi) ? kEpiBytes : 0u;   // epilogue slabs (1024 B aligned: ring_bytes is a multiple of 1024)
+    const uint32_t epi_bytes = (!SPLIT && p.epi) ? epi_slab_bytes(NEPI, p.epi_gw) : 0u;   // 1024 B aligned: ring_bytes is a multiple of 1024
     const uint32_t slabs = base + ring_bytes;
     const uint32_t bars = slabs + epi_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
     const uint32_t tmem_slot = bars + 16u * S + 32u;
     const uint32_t bar_pfull = bars + 16u * S + 48u, bar_pempty = bars + 16u * S + 80u;
+    const uint32_t bar_w = bar_pfull + 24u;                                         // resident-W barrier (patch slot 3 is never used)
     float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + epi_bytes + 16u * S + 112u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* dbg = (p.dbg && blockIdx.x < 4096) ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
 #define Y4_STAMP(i) do { if (dbg) dbg[i] = clock64(); } while (0)
+    pdl_launch_dependents();
     if (threadIdx.x == 0) { Y4_STAMP(0); if (dbg) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); dbg[15] = sm; long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[14] = gt; } }
 
     if (warp == 0 && lane == 0) {
@@ -506,7 +518,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
         tma_prefetch_desc(&p.tmA[0]);
         if (p.mode == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
-        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 4); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, NEPI); }
         for (int a = 0; a < 4; a++) { mbar_init(bar_pfull + 8u * a, 1); mbar_init(bar_pempty + 8u * a, 1); }
         if (p.mode == 3) tma_prefetch_desc(&p.tmA[1]);
         if (p.epi) tma_prefetch_desc(&p.tmOut);
@@ -516,12 +528,14 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
     float* sscale = sbias + p.bias_n;
     // non-split mish layers keep b * log2(e) (act_fast)
     const float bmul = (!SPLIT && p.act == 2) ? 1.4426950408889634f : 1.0f;
-    if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 128) { sbias[i] = p.bias[i] * bmul; sscale[i] = p.wscale ? p.wscale[i] : 1.0f; }
+    // (weights, biases and scales are written once at load time, never by a preceding kernel: safe before pdl_wait)
+    if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 32 * NEPI) { sbias[i] = p.bias[i] * bmul; sscale[i] = p.wscale ? p.wscale[i] : 1.0f; }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();                                             // everything below reads or writes activations
     if (threadIdx.x == 0) Y4_STAMP(1);
 
     if (warp == 0) {
@@ -567,7 +581,17 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     }
                     if (j == 0) Y4_STAMP(3);
                 }
-            } else
+            } else {
+            if (p.bres) {
+                // the whole weight matrix (n_tiles == 1) stays in shared memory for the life of the CTA: num_kb boxes, one barrier
+                mbar_expect_tx(bar_w, (uint32_t)p.num_kb * (uint32_t)B_BYTES);
+                for (int kb = 0; kb < p.num_kb; kb++) {
+                    int tap, cb;
+                    if (p.mode == 1 && p.ksize == 3) { cb = kb / 9; tap = kb - cb * 9; }
+                    else { tap = kb / p.kb_per_tap; cb = kb - tap * p.kb_per_tap; }
+                    tma_load_2d(base + (uint32_t)kb * (uint32_t)B_BYTES, &p.tmW, bar_w, (tap * p.kb_per_tap + cb) * BK, 0);
+                }
+            }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
                 const TileCoord tc = decode_tile<BN>(p, tile);
                 // a stage holds `group` k-blocks behind ONE barrier: the per-barrier latency of the single issuing
@@ -578,7 +602,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     mbar_wait_t(bar_empty + 8u * s, ph ^ 1u, dbg ? &w_empty : nullptr);
                     const uint32_t fb = bar_full + 8u * s;
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
-                    mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES) * (SPLIT ? 2u : 1u));
+                    mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (p.bres ? 0u : (uint32_t)B_BYTES)) * (SPLIT ? 2u : 1u));
                     for (int kk = 0; kk < gcount; kk++) {
                         const int kb = kb0 + kk;
                         // K order.  flat 3x3: channel block outer, tap inner -- the order the A-patch mode (3) needs, so both
@@ -588,7 +612,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                         else { tap = kb / p.kb_per_tap; cb = kb - tap * p.kb_per_tap; }
                         const int c0 = cb * BK;
                         const int wcol = (tap * p.kb_per_tap + cb) * BK;
-                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * SBYTES;
+                        const uint32_t sa = ring0 + (s * (uint32_t)G + (uint32_t)kk) * ASTRIDE;
                         if (p.mode == 1) {
                             int shift = 0;
                             if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
@@ -597,7 +621,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                             const int kh = tap / 3, kw = tap - kh * 3;
                             tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
                         }
-                        tma_load_2d(sa + A_BYTES, &p.tmW, fb, wcol, tc.n0);
+                        if (!p.bres) tma_load_2d(sa + A_BYTES, &p.tmW, fb, wcol, tc.n0);
                         if (SPLIT) {
                             const uint32_t sl = sa + STAGE_BYTES;
                             if (p.mode == 1) {
@@ -615,6 +639,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                 }
                 if (tile == (int)blockIdx.x) Y4_STAMP(3);
             }
+            }
             if (dbg) dbg[12] = w_empty;
         }
     } else if (warp == 1) {
@@ -623,6 +648,7 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             uint32_t it = 0, ti = 0, pit = 0;
             long long w_full = 0, w_tempty = 0, w_pfull = 0;
             const long long t_mma0 = clock64();
+            if (p.bres) { mbar_wait(bar_w, 0u); tc_fence_after(); }
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
                 const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
                 mbar_wait_t(bar_tempty + 8u * as, aph ^ 1u, dbg ? &w_tempty : nullptr);   // epilogue has drained this accumulator stage
@@ -660,9 +686,9 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
                     if (it == 0) Y4_STAMP(4);
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
                     for (int kk = 0; kk < gcount; kk++) {
-                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * SBYTES;
+                        const uint32_t sa = ring0 + (s * (uint32_t)G + (uint32_t)kk) * ASTRIDE;
                         const uint64_t da = make_smem_desc<SWZ>(sa);
-                        const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
+                        const uint64_t db = make_smem_desc<SWZ>(p.bres ? base + (uint32_t)(kb0 + kk) * (uint32_t)B_BYTES : sa + A_BYTES);
                         if (SPLIT) {
                             // (a_hi + a_lo)(b_hi + b_lo) without the a_lo*b_lo term (2^-22 relative): small terms first
                             const uint64_t la = make_smem_desc<SWZ>(sa + STAGE_BYTES);
@@ -687,13 +713,21 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             if (dbg) { dbg[9] = w_full; dbg[10] = w_tempty; dbg[11] = clock64() - t_mma0; dbg[13] = w_pfull; }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31; with NEPI = 8, warps w and w+4 alternate 32-column groups =====
         const int q = warp & 3;
+        const int set = (warp - 2) >> 2;                    // 0, or 1 for the second set of four warps
+        constexpr int NSETS = NEPI / 4;
+        constexpr int NCH = BN / 32;                        // 32-column groups per tile
         const int r = q * 32 + lane;                        // row of the tile
         uint32_t ti = 0, sit = 0;                           // sit: slab groups issued by this warp (epi = 1)
-        if (!SPLIT && p.epi && p.res && (int)blockIdx.x < p.num_tiles) {
+        const bool slab_epi = !SPLIT && p.epi;
+        const bool has_res = p.res != nullptr;
+        const bool gw64 = p.epi_gw == 64;                   // 64-channel groups: NEPI == 4 only (host)
+        const uint32_t slab_bytes = gw64 ? 2u * kSlabBytes : kSlabBytes;
+        const uint32_t my_slabs = slabs + (uint32_t)(warp - 2) * 2u * slab_bytes;
+        if (slab_epi && has_res && (int)blockIdx.x < p.num_tiles) {
             const TileCoord t0 = decode_tile<BN>(p, (int)blockIdx.x);
-            res_prefetch(p, slabs + (uint32_t)q * 2u * kSlabBytes, t0.m0 + q * 32, t0.n0, lane, p.epi_cols == 64);
+            res_prefetch(p, my_slabs, t0.m0 + q * 32, t0.n0 + 32 * set, lane, gw64);
         }
         for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
             const TileCoord tc = decode_tile<BN>(p, tile);
@@ -721,43 +755,70 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             tc_fence_after();
             if (ti == 0 && threadIdx.x == 64) Y4_STAMP(6);
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN;
-            uint32_t va[32], vb[32];
-            tmem_ld32_issue(tacc, va);
-            if (!SPLIT && p.epi) {
-                const bool cols64 = p.epi_cols == 64;
-                const bool has_res = p.res != nullptr;
-                const uint32_t my_slabs = slabs + (uint32_t)q * 2u * kSlabBytes;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 64, sit++) {
-                    const uint32_t slab = my_slabs + (sit & 1u) * kSlabBytes;
-                    if (has_res) { cp_async_wait_all(); __syncwarp(); }      // this group's skip tile is in the slab
-                    tmem_ld_wait(va);
-                    tmem_ld32_issue(tacc + (uint32_t)(c0 + 32), vb);
-                    epi_half(p, va, sbias + tc.n0 + c0, slab, lane, 0, valid, has_res, cols64);
-                    __syncwarp();
-                    tmem_ld_wait(vb);
-                    if (c0 + 64 < BN) tmem_ld32_issue(tacc + (uint32_t)(c0 + 64), va);
-                    else { tc_fence_before(); if (lane == 0) mbar_arrive(bar_tempty + 8u * as); }   // accumulator stage drained
-                    if (cols64) epi_half(p, vb, sbias + tc.n0 + c0 + 32, slab, lane, 1, valid, has_res, cols64);
-                    // the previous group's store has had a whole group of math to read its slab: free it, refill it with
-                    // the next group's skip tile, then hand this slab to the TMA
-                    if (lane == 0) bulk_wait_read<0>();
+            uint32_t va[32];
+            [[maybe_unused]] uint32_t vb[32];
+            if (slab_epi) {
+                // one 32-column chunk of a 32- or 64-channel group:
+                // (skip tile landed) -> math -> slab -> [previous store drained -> prefetch next skip tile] -> TMA store
+                auto do_group = [&](const uint32_t (&v)[32], int k) {
+                    if (tc.n0 + 32 * k >= p.cout_store) return;              // channel padding (cout = 32 in a 64-wide tile)
+                    const int h = gw64 ? (k & 1) : 0;
+                    const bool last = !gw64 || h == 1 || tc.n0 + 32 * (k + 1) >= p.cout_store;
+                    const uint32_t slab = my_slabs + (sit & 1u) * slab_bytes;
+                    if (has_res && h == 0) { cp_async_wait_all(); __syncwarp(); }
+                    epi_group(p, v, sbias + tc.n0 + 32 * k, slab, lane, h, valid, has_res, gw64);
+                    if (!last) return;
+                    if (lane == 0) bulk_wait_read<0>();                      // the previous group's store has drained its slab
                     __syncwarp();
                     if (has_res) {
-                        int nc0 = c0 + 64, ntile = tile;
-                        if (nc0 >= BN) { nc0 = 0; ntile = tile + (int)gridDim.x; }
+                        int nk = gw64 ? k + 1 : k + NSETS, ntile = tile;
+                        if (nk >= NCH || tc.n0 + 32 * nk >= p.cout_store) { nk = set; ntile = tile + (int)gridDim.x; }
                         if (ntile < p.num_tiles) {
                             const TileCoord tn = decode_tile<BN>(p, ntile);
-                            res_prefetch(p, my_slabs + ((sit + 1u) & 1u) * kSlabBytes, tn.m0 + q * 32, tn.n0 + nc0, lane, cols64);
+                            res_prefetch(p, my_slabs + ((sit + 1u) & 1u) * slab_bytes, tn.m0 + q * 32, tn.n0 + 32 * nk, lane, gw64);
                         }
                     }
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tma_store_2d(&p.tmOut, slab, tc.n0 + c0, (int)(tc.m0 + q * 32)); bulk_commit(); }
+                    if (lane == 0) { tma_store_2d(&p.tmOut, slab, tc.n0 + 32 * (k - h), (int)(tc.m0 + q * 32)); bulk_commit(); }
+                    sit++;
+                };
+                auto release_acc = [&]() { tc_fence_before(); if (lane == 0) mbar_arrive(bar_tempty + 8u * as); };
+                if constexpr (NEPI == 8) {
+                    // lean loop (fits two 320-thread CTAs per SM): one register buffer, no software pipelining of the TMEM
+                    // loads -- sixteen epilogue warps per SM hide that latency by switching warps instead
+#pragma unroll 1
+                    for (int k = set; k < NCH; k += NSETS) {
+                        tmem_ld32_issue(tacc + (uint32_t)(32 * k), va);
+                        tmem_ld_wait(va);
+                        if (k + NSETS >= NCH) release_acc();
+                        do_group(va, k);
+                        __syncwarp();
+                    }
+                    if (ti == 0 && threadIdx.x == 64) Y4_STAMP(7);
+                    continue;
+                } else {
+                tmem_ld32_issue(tacc + (uint32_t)(32 * set), va);
+#pragma unroll 1
+                for (int k = set; k < NCH; k += 2 * NSETS) {
+                    const int k2 = k + NSETS;
+                    tmem_ld_wait(va);
+                    if (k2 < NCH) tmem_ld32_issue(tacc + (uint32_t)(32 * k2), vb); else release_acc();
+                    do_group(va, k);
+                    __syncwarp();
+                    if (k2 < NCH) {
+                        tmem_ld_wait(vb);
+                        if (k2 + NSETS < NCH) tmem_ld32_issue(tacc + (uint32_t)(32 * (k2 + NSETS)), va); else release_acc();
+                        do_group(vb, k2);
+                        __syncwarp();
+                    }
                 }
                 if (ti == 0 && threadIdx.x == 64) Y4_STAMP(7);
                 continue;
+                }
             }
+            if constexpr (NEPI == 4) {
+            tmem_ld32_issue(tacc, va);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 64) {
                 tmem_ld_wait(va);
@@ -773,8 +834,9 @@ __global__ void __launch_bounds__(kTcThreads) conv_tc_kernel(const __grid_consta
             tc_fence_before();
             if (lane == 0) mbar_arrive(bar_tempty + 8u * as);
             if (ti == 0 && threadIdx.x == 64) Y4_STAMP(7);
+            }
         }
-        if (!SPLIT && p.epi && lane == 0) bulk_wait_all();  // the slabs must outlive the TMA reads, the writes the kernel
+        if (slab_epi && lane == 0) bulk_wait_all();         // the slabs must outlive the TMA reads, the writes the kernel
     }
     tc_fence_before();
     __syncthreads();
@@ -813,20 +875,31 @@ inline bool encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* d
     return true;
 }
 
-template <int BN, int BK, bool SPLIT>
+inline bool pdl_enabled() {
+    static const bool on = !(getenv("Y4_PDL") && getenv("Y4_PDL")[0] == '0');
+    return on;
+}
+
+template <int BN, int BK, bool SPLIT, int NEPI>
 inline cudaError_t launch_inst2(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
-    static size_t configured = 0;
-    if (pl.smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, SPLIT, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
         if (e != cudaSuccess) return e;
-        configured = 220 * 1024;
+        configured = true;
     }
-    conv_tc_kernel<BN, BK, SPLIT><<<grid, kTcThreads, pl.smem, st>>>(pl.p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(64 + 32 * NEPI); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, BK, SPLIT, NEPI>, pl.p);
 }
 template <int BN, int BK>
 inline cudaError_t launch_inst(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
-    return pl.p.split ? launch_inst2<BN, BK, true>(pl, grid, st) : launch_inst2<BN, BK, false>(pl, grid, st);
+    if (pl.p.split) return launch_inst2<BN, BK, true, 4>(pl, grid, st);
+    return pl.nepi == 8 ? launch_inst2<BN, BK, false, 8>(pl, grid, st) : launch_inst2<BN, BK, false, 4>(pl, grid, st);
 }
 
 inline int sm_count() {
@@ -864,7 +937,8 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 }
 
 // returns kernel kind (0 = not eligible -> CUDA-core kernel, 1 = flat GEMM, 2 = strided box), <0 on error
-inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0, int group = 1, int epi = 0) {
+inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0, int group = 1,
+                   int epi = 0, int nepi = 4, int bres = 0, int gw = 32) {
     if (d.raw_in) return 0;                                   // conv 0 (cin = 3): CUDA-core kernel
     const int bk = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 0);
     if (!bk) return 0;
@@ -883,6 +957,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     if (d.split && (patch || bk != 64 && bk != 32)) return 0;
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
     p.act = d.act; p.out_f32 = d.out_f32; p.upsample = d.upsample;
+    if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);      // timing experiments only (wrong results)
     p.cout_store = d.out_f32 ? d.cout_pad : d.cout;
     p.ksize = d.k;
     p.kb_per_tap = d.cin / bk;
@@ -939,23 +1014,31 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
             }
     }
     size_t epi_bytes = 0;
+    if (nepi != 4 && (nepi != 8 || !epi)) return 0;
+    P.nepi = nepi;
     if (epi) {
-        // slab epilogue: flat tiles, fp16 output written in place (no upsample), whole 64-channel groups (or one of 32)
-        if (P.kind != 1 || d.out_f32 || d.upsample || d.split || !(p.cout_store % 64 == 0 || (p.cout_store == 32 && bn == 64))) return 0;
-        p.epi = 1;
-        p.epi_cols = p.cout_store % 64 == 0 ? 64 : 32;
+        // slab epilogue: flat tiles, fp16 output written in place (no upsample), whole 32- or 64-channel groups
+        if (P.kind != 1 || d.out_f32 || d.upsample || d.split || p.cout_store % gw != 0) return 0;
+        if (gw != 32 && (gw != 64 || nepi != 4)) return 0;
+        p.epi = 1; p.epi_gw = gw;
         p.rows_alloc = (long long)d.max_batch * in_Hp * in_Wp;
         cuuint64_t dims[2] = {(cuuint64_t)p.cout_store, (cuuint64_t)p.rows_alloc};
         cuuint64_t str[1] = {(cuuint64_t)d.out_ld * 2};
-        cuuint32_t box[2] = {(cuuint32_t)p.epi_cols, 32};
+        cuuint32_t box[2] = {(cuuint32_t)gw, 32};
         char* out_base = reinterpret_cast<char*>(d.out) + (size_t)d.out_choff * 2;
-        if (!encode_map(&p.tmOut, out_base, 2, dims, str, box, p.epi_cols * 2, err)) return -1;
-        epi_bytes = kEpiBytes;
-        if ((size_t)smem_budget_kb * 1024 <= epi_bytes + 16 * 1024) return 0;
+        if (!encode_map(&p.tmOut, out_base, 2, dims, str, box, gw * 2, err)) return -1;
+        epi_bytes = epi_slab_bytes(nepi, gw);
     }
-    size_t stage_bytes = ((size_t)128 * bk * 2 + (size_t)bn * bk * 2) * (d.split ? 2 : 1);
-    size_t ring_fixed = 0;
-    if (!patch && getenv("Y4_FORCE_PATCH") && P.kind == 1 && d.k == 3 && bk == 64) { patch = 1; if (smem_budget_kb < 200) smem_budget_kb = 200; }
+    size_t wres_bytes = 0;
+    if (bres) {
+        // resident weights: one N tile, no split planes, not the patch mode (whose ring holds B tiles)
+        wres_bytes = (size_t)bn * K * 2;
+        if (d.cout_pad != bn || d.split || patch || wres_bytes > 96 * 1024) return 0;
+        p.bres = 1;
+    }
+    size_t stage_bytes = bres ? (size_t)128 * bk * 2 : ((size_t)128 * bk * 2 + (size_t)bn * bk * 2) * (d.split ? 2 : 1);
+    size_t ring_fixed = wres_bytes;
+    if (!patch && getenv("Y4_FORCE_PATCH") && P.kind == 1 && d.k == 3 && bk == 64 && !bres) { patch = 1; if (smem_budget_kb < 200) smem_budget_kb = 200; }
     if (patch) {
         // A-patch reuse (mode 3): 3x3 stride 1, 64-channel blocks; patch = 130 + 2*Wp rows, loaded as 32-row TMA boxes
         if (P.kind != 1 || d.k != 3 || bk != 64) return 0;
@@ -973,28 +1056,28 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
         if (!encode_map(&p.tmA[1], in_base, 2, dims, str, box, swz, err)) return -1;
         ring_fixed = (size_t)p.patch_slots * p.patch_bytes;
         stage_bytes = (size_t)bn * bk * 2;                            // the ring holds B tiles only
-        if ((size_t)smem_budget_kb * 1024 < ring_fixed + 2 * stage_bytes + epi_bytes) return 0;
     }
     if (patch || group < 1) group = 1;
     if (group > p.num_kb) group = p.num_kb;
     p.group = group;
     stage_bytes *= (size_t)group;
-    int S = (int)(((size_t)smem_budget_kb * 1024 - ring_fixed - epi_bytes) / stage_bytes);   // default budget ~100 KB: two CTAs share an SM
-    if (S < 2) { if (group > 1) return 0; S = 2; }
+    // the ring runs across tile boundaries (persistent CTA), so it may be deeper than one tile's k-blocks: for the K = 64
+    // layers that is what keeps several tiles of activations in flight
+    // smem_budget_kb bounds the CTA's TOTAL dynamic shared memory (112 KB: two CTAs per SM, 224 KB: one)
+    const size_t fixed = 1024 + ring_fixed + epi_bytes + 16 * 8 + 112 + 8 * (size_t)d.cout_pad;
+    const size_t budget = (size_t)smem_budget_kb * 1024;
+    int S = budget > fixed ? (int)((budget - fixed) / stage_bytes) : 0;
     if (S > 8) S = 8;
-    const int max_useful = patch ? 9 * p.kb_per_tap : (p.num_kb + group - 1) / group;
-    if (S > max_useful && group == 1) S = max_useful;
-    if (S > max_useful + 1) S = max_useful + 1;
-    if (S < 2) S = 2;
+    if (S < 2) { if (group > 1 || patch || bres || epi) return 0; S = 2; }      // plain plans always get a double buffer
     P.stages = S; p.stages = S;
     p.n_tiles = (p.cout_store + bn - 1) / bn;
     p.bias_n = d.cout_pad;
     P.smem = 1024 + ring_fixed + S * stage_bytes + epi_bytes + 16 * S + 112 + 8 * (size_t)p.bias_n;   // bias + weight-scale arrays
-    if (P.smem > 220 * 1024) { *err = "smem budget exceeded"; return -1; }
+    if (P.smem > 225 * 1024) { *err = "smem budget exceeded"; return -1; }
     int cps = (int)((227 * 1024) / (P.smem + 1024));            // +1 KB: per-CTA reserved shared memory
     const int tmem_cols = 2 * bn;
     if (cps > 512 / tmem_cols) cps = 512 / tmem_cols;            // two accumulator stages per CTA must all fit in TMEM
-    if (cps > 2) cps = 2;                                        // register file: ~140 regs x 192 threads
+    if (cps > 2) cps = 2;                                        // register file: 168 regs x 192 threads
     if (cps < 1) cps = 1;
     if (d.split) cps = 1;                                       // split kernels use > 170 registers/thread
     P.ctas_per_sm = cps;

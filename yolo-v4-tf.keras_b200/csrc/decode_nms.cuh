@@ -11,7 +11,6 @@ namespace y4 {
 constexpr int kCandCap = 8192;     // Y4_MAX_CANDIDATES
 constexpr int kSelCap = 8192;      // >= num_classes * max_boxes
 constexpr int kMaxBoxesCap = 128;  // max_boxes upper bound (per-warp selected list in smem)
-constexpr int kNmsThreads = 1024;
 
 struct DecodeParams {
     const float* head[3];
@@ -130,28 +129,18 @@ __device__ __forceinline__ float iou_tf(const float4 a, const float4 b) {
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
 }
 
-__device__ __forceinline__ void bitonic_sort_smem(unsigned long long* keys, int P) {
-    for (int k = 2; k <= P; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < P; i += blockDim.x) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const unsigned long long a = keys[i], b = keys[ixj];
-                    const bool asc = (i & k) == 0;
-                    if ((a > b) == asc) { keys[i] = b; keys[ixj] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
-}
-
 struct NmsParams {
-    const unsigned long long* cand_keys;   // [batch][kCandCap]
+    const unsigned long long* cand_keys;   // [batch][kCandCap]   decode output, unordered
     const int* cand_count;                 // [batch]
     const float4* boxes;                   // [batch][N]
     int N, nc, max_boxes;
     float iou_thr;
+    // workspace
+    unsigned long long* bucket_keys;       // [batch][kCandCap]   grouped by class (order inside a class arbitrary)
+    unsigned long long* sorted_keys;       // [batch][kCandCap]   only used by class segments longer than kClassSmemKeys
+    int* seg_start;                        // [batch][257]        first bucket position of each class
+    unsigned long long* win_keys;          // [batch][nc][max_boxes]  per-class NMS survivors as merge keys, score descending
+    int* nwin;                             // [batch][256]
     float* out_boxes;      // [batch][max_boxes][4]
     float* out_scores;     // [batch][max_boxes]
     float* out_classes;    // [batch][max_boxes]
@@ -160,135 +149,149 @@ struct NmsParams {
     int* overflow;         // set to 1 if any image exceeded kCandCap
 };
 
-// One CTA per image.  Candidates are grouped by class with a counting sort (histogram + scatter), each class segment
-// is ordered (score desc, box asc) by a warp rank-sort (segments are short: ~candidates/80), one warp per class runs the
-// greedy suppression (boxes fetched 32 at a time and broadcast by shuffle; every lane tests the candidate against a
-// strided subset of the already-selected boxes, warp vote), and the per-class winner lists - already in score order -
-// are merged by global ranking (score desc, class asc, box asc) into the top max_boxes, clipped to [0,1].
-// Segments longer than kRankSortMax are rank-sorted by the whole CTA (cost ~ L^2 / 1024 per thread).
-constexpr int kRankSortMax = 256;
+// combined_non_max_suppression as three small kernels whose parallelism is (image, class), not image:
+//   nms_bucket_kernel  one CTA per image: counting sort of the candidate keys by class (smem histogram + scatter)
+//   nms_class_kernel   one CTA per (image, class): rank sort of the segment (score desc, box asc; keys are unique),
+//                      then warp 0 runs TF's greedy scan (iou > thr strict, against already selected boxes)
+//   nms_merge_kernel   one CTA per image: every survivor finds its global rank (score desc, class asc, box asc) by a
+//                      binary search in each class list; ranks < max_boxes are the output, clipped to [0,1]
+constexpr int kBucketThreads = 1024;
+constexpr int kClassThreads = 128;
+constexpr int kClassSmemKeys = 1024;
+constexpr int kMergeThreads = 1024;
+constexpr size_t kMergeSmemBytes = (size_t)kSelCap * 8;
 
-__global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
-    extern __shared__ __align__(16) unsigned char nms_smem[];
-    unsigned long long* bufA = reinterpret_cast<unsigned long long*>(nms_smem);      // keys, finally class-sorted
-    unsigned long long* bufB = bufA + kCandCap;                                       // scatter target, then winner lists
-    float4* wbox = reinterpret_cast<float4*>(bufB + kSelCap);                         // [32 warps][kMaxBoxesCap]
-    __shared__ int hist[256], start[257], cursor[256], nwin[256];
-    __shared__ int big;
-
-    const int img = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__global__ void __launch_bounds__(kBucketThreads) nms_bucket_kernel(NmsParams p) {
+    __shared__ int hist[256], cursor[256];
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     int cnt = p.cand_count[img];
     if (cnt > kCandCap) { if (tid == 0) *p.overflow = 1; cnt = kCandCap; }
-    if (tid < 256) { hist[tid] = 0; nwin[tid] = 0; }
-    if (tid == 0) big = 0;
+    if (tid < 256) hist[tid] = 0;
     __syncthreads();
-    for (int i = tid; i < cnt; i += blockDim.x) {
-        const unsigned long long k = p.cand_keys[(long long)img * kCandCap + i];
-        bufA[i] = k;
-        atomicAdd(&hist[(int)(k >> 56)], 1);
+    constexpr int PER = kCandCap / kBucketThreads;
+    unsigned long long k[PER];
+#pragma unroll
+    for (int r = 0; r < PER; r++) {
+        const int i = tid + r * kBucketThreads;
+        if (i < cnt) { k[r] = p.cand_keys[(long long)img * kCandCap + i]; atomicAdd(&hist[(int)(k[r] >> 56)], 1); }
     }
     __syncthreads();
-    if (tid == 0) {
-        int acc = 0, mx = 0;
-        for (int c = 0; c < p.nc; c++) { start[c] = acc; cursor[c] = acc; acc += hist[c]; mx = hist[c] > mx ? hist[c] : mx; }
-        start[p.nc] = acc;
-        big = mx > kRankSortMax;
+    if (tid < 32) {                                        // exclusive scan of the 256 bins, 8 per lane
+        int v[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { v[j] = hist[lane * 8 + j]; s += v[j]; }
+        int incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        int run = incl - s;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { cursor[lane * 8 + j] = run; p.seg_start[img * 257 + lane * 8 + j] = run; run += v[j]; }
+        if (lane == 31) p.seg_start[img * 257 + 256] = run;
     }
     __syncthreads();
-    for (int i = tid; i < cnt; i += blockDim.x) {
-        const unsigned long long k = bufA[i];
-        bufB[atomicAdd(&cursor[(int)(k >> 56)], 1)] = k;
+#pragma unroll
+    for (int r = 0; r < PER; r++) {
+        const int i = tid + r * kBucketThreads;
+        if (i < cnt) p.bucket_keys[(long long)img * kCandCap + atomicAdd(&cursor[(int)(k[r] >> 56)], 1)] = k[r];
+    }
+}
+
+__global__ void __launch_bounds__(kClassThreads) nms_class_kernel(NmsParams p) {
+    __shared__ unsigned long long sin[kClassSmemKeys], ssorted[kClassSmemKeys];
+    __shared__ float4 selbox[kMaxBoxesCap];
+    const int img = blockIdx.x / p.nc, c = blockIdx.x - img * p.nc;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int lo = p.seg_start[img * 257 + c], L = p.seg_start[img * 257 + c + 1] - lo;
+    if (L == 0) { if (tid == 0) p.nwin[img * 256 + c] = 0; return; }
+    const unsigned long long* in = p.bucket_keys + (long long)img * kCandCap + lo;
+    unsigned long long* sorted = p.sorted_keys + (long long)img * kCandCap + lo;
+    if (L <= kClassSmemKeys) {
+        for (int i = tid; i < L; i += kClassThreads) sin[i] = in[i];
+        __syncthreads();
+        in = sin; sorted = ssorted;
+    }
+    for (int i = tid; i < L; i += kClassThreads) {        // keys are unique (box index): rank = number of smaller keys
+        const unsigned long long k = in[i];
+        int r = 0;
+        for (int j = 0; j < L; j++) r += in[j] < k;
+        sorted[r] = k;
     }
     __syncthreads();
-    // rank sort inside each class segment: keys are unique (box index), rank = #smaller keys.
-    // short segments: one warp each; segments longer than kRankSortMax: the whole CTA, one segment after the other
-    for (int c = warp; c < p.nc; c += (kNmsThreads >> 5)) {
-        const int lo = start[c], L = hist[c];
-        if (L > kRankSortMax) continue;
-        for (int i = lane; i < L; i += 32) {
-            const unsigned long long k = bufB[lo + i];
-            int r = 0;
-            for (int j = 0; j < L; j++) r += bufB[lo + j] < k;
-            bufA[lo + r] = k;
-        }
-    }
-    if (big) {
-        for (int c = 0; c < p.nc; c++) {
-            const int lo = start[c], L = hist[c];
-            if (L <= kRankSortMax) continue;                     // block-uniform
-            for (int i = tid; i < L; i += blockDim.x) {
-                const unsigned long long k = bufB[lo + i];
-                int r = 0;
-                for (int j = 0; j < L; j++) r += bufB[lo + j] < k;
-                bufA[lo + r] = k;
-            }
-        }
-    }
-    __syncthreads();
-    const unsigned long long* keys = bufA;
+    if (tid >= 32) return;
 
     const float4* boxes = p.boxes + (long long)img * p.N;
-    float4* mybox = wbox + warp * kMaxBoxesCap;
-    for (int c = warp; c < p.nc; c += (kNmsThreads >> 5)) {
-        const int lo = start[c], hi = start[c] + hist[c];
-        unsigned long long* win = bufB + (size_t)c * p.max_boxes;       // winners of class c, in score order
-        int nsel = 0;
-        for (int base = lo; base < hi && nsel < p.max_boxes; base += 32) {
-            const int mine = base + lane;
-            unsigned long long mykey = 0ull;
-            float4 mybx = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (mine < hi) { mykey = keys[mine]; mybx = boxes[(int)(mykey & 0xFFFFFFull)]; }
-            const int cnt32 = hi - base < 32 ? hi - base : 32;
-            for (int j = 0; j < cnt32 && nsel < p.max_boxes; j++) {
-                float4 b;
-                b.x = __shfl_sync(0xffffffffu, mybx.x, j); b.y = __shfl_sync(0xffffffffu, mybx.y, j);
-                b.z = __shfl_sync(0xffffffffu, mybx.z, j); b.w = __shfl_sync(0xffffffffu, mybx.w, j);
-                const unsigned long long key = __shfl_sync(0xffffffffu, mykey, j);
-                bool sup = false;
-                for (int t = lane; t < nsel; t += 32) sup |= iou_tf(b, mybox[t]) > p.iou_thr;   // strict >
-                if (!__any_sync(0xffffffffu, sup)) {
-                    if (lane == 0) {
-                        mybox[nsel] = b;
-                        const float score = __uint_as_float(~(unsigned)((key >> 24) & 0xFFFFFFFFull));
-                        win[nsel] = merge_key(c, score, (int)(key & 0xFFFFFFull));
-                    }
-                    nsel++;
-                    __syncwarp();
+    unsigned long long* win = p.win_keys + ((long long)img * p.nc + c) * p.max_boxes;
+    int nsel = 0;
+    for (int base = 0; base < L && nsel < p.max_boxes; base += 32) {
+        const int mine = base + lane;
+        unsigned long long mykey = 0ull;
+        float4 mybx = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mine < L) { mykey = sorted[mine]; mybx = boxes[(int)(mykey & 0xFFFFFFull)]; }
+        const int cnt32 = L - base < 32 ? L - base : 32;
+        for (int j = 0; j < cnt32 && nsel < p.max_boxes; j++) {
+            float4 b;
+            b.x = __shfl_sync(0xffffffffu, mybx.x, j); b.y = __shfl_sync(0xffffffffu, mybx.y, j);
+            b.z = __shfl_sync(0xffffffffu, mybx.z, j); b.w = __shfl_sync(0xffffffffu, mybx.w, j);
+            const unsigned long long key = __shfl_sync(0xffffffffu, mykey, j);
+            bool sup = false;
+            for (int t = lane; t < nsel; t += 32) sup |= iou_tf(b, selbox[t]) > p.iou_thr;   // strict >
+            if (!__any_sync(0xffffffffu, sup)) {
+                if (lane == 0) {
+                    selbox[nsel] = b;
+                    const float score = __uint_as_float(~(unsigned)((key >> 24) & 0xFFFFFFFFull));
+                    win[nsel] = merge_key(c, score, (int)(key & 0xFFFFFFull));
                 }
+                nsel++;
+                __syncwarp();
             }
         }
-        if (lane == 0) nwin[c] = nsel;
     }
-    __syncthreads();
+    if (lane == 0) p.nwin[img * 256 + c] = nsel;
+}
 
-    // merge: compact the per-class winner lists, then every winner computes its global rank (number of smaller merge
-    // keys = score desc, class asc, box asc; keys are unique) and the first max_boxes ranks are the output order
+__global__ void __launch_bounds__(kMergeThreads) nms_merge_kernel(NmsParams p) {
+    extern __shared__ __align__(16) unsigned char merge_smem[];
+    unsigned long long* wk = reinterpret_cast<unsigned long long*>(merge_smem);     // survivors, class-major, ascending inside a class
+    __shared__ int nw[256], off[257];
     __shared__ unsigned long long outkeys[kMaxBoxesCap];
-    __shared__ int nout;
-    if (tid == 0) {
-        int acc = 0;
-        for (int c = 0; c < p.nc; c++) { cursor[c] = acc; acc += nwin[c]; }
-        nout = acc;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 256) nw[tid] = tid < p.nc ? p.nwin[img * 256 + tid] : 0;
+    __syncthreads();
+    if (tid < 32) {
+        int v[8], s = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { v[j] = nw[lane * 8 + j]; s += v[j]; }
+        int incl = s;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
+        int run = incl - s;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { off[lane * 8 + j] = run; run += v[j]; }
+        if (lane == 31) off[256] = run;
     }
     __syncthreads();
-    const int ntot = nout;
-    for (int c = warp; c < p.nc; c += (kNmsThreads >> 5))
-        for (int i = lane; i < nwin[c]; i += 32) bufA[cursor[c] + i] = bufB[(size_t)c * p.max_boxes + i];
+    const int ntot = off[256];
+    for (int c = warp; c < p.nc; c += (kMergeThreads >> 5)) {
+        const unsigned long long* src = p.win_keys + ((long long)img * p.nc + c) * p.max_boxes;
+        for (int i = lane; i < nw[c]; i += 32) wk[off[c] + i] = src[i];
+    }
     __syncthreads();
-    for (int i = tid; i < ntot; i += blockDim.x) {
-        const unsigned long long k = bufA[i];
+    for (int i = tid; i < ntot; i += kMergeThreads) {
+        const unsigned long long k = wk[i];
         int r = 0;
-        for (int j = 0; j < ntot && r < p.max_boxes; j++) r += bufA[j] < k;
+        for (int c = 0; c < p.nc && r < p.max_boxes; c++) {
+            int lo = 0, hi = nw[c];                        // lower bound of k in class c's ascending list
+            const unsigned long long* a = wk + off[c];
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < k) lo = mid + 1; else hi = mid; }
+            r += lo;
+        }
         if (r < p.max_boxes) outkeys[r] = k;
     }
     __syncthreads();
-    if (tid == 0) nout = ntot < p.max_boxes ? ntot : p.max_boxes;
-    __syncthreads();
-
-    const int nvalid = nout;
+    const int nvalid = ntot < p.max_boxes ? ntot : p.max_boxes;
+    const float4* boxes = p.boxes + (long long)img * p.N;
     if (tid == 0) p.out_valid[img] = nvalid;
-    for (int k = tid; k < p.max_boxes; k += blockDim.x) {
+    for (int k = tid; k < p.max_boxes; k += kMergeThreads) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         float score = 0.f, cls = 0.f;
         int idx = -1;
@@ -308,7 +311,5 @@ __global__ void __launch_bounds__(kNmsThreads) nms_kernel(NmsParams p) {
         p.out_idx[o] = idx;
     }
 }
-
-constexpr size_t kNmsSmemBytes = (size_t)(kCandCap + kSelCap) * 8 + (size_t)(kNmsThreads / 32) * kMaxBoxesCap * 16;
 
 }  // namespace y4

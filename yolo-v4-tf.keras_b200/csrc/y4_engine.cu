@@ -68,6 +68,7 @@ struct ConvOp {
     __half* d_w16k32 = nullptr; // conv 0 only: [32][32], K zero-padded 27 -> 32 (conv0_tc.cuh)
     int kind = 0;              // 0 simt, 1 tc flat, 2 tc box
     TcConvPlan tc;             // tensor maps + tile config (conv_tc.cuh)
+    TcConvDesc desc{};         // what tc was planned from (the autotuner re-plans candidates from it)
     std::string out_name;
 };
 struct Step { int type; int conv; };   // type 0 conv, 1 spp
@@ -92,6 +93,8 @@ struct y4_engine {
     int head_buf[3] = {-1, -1, -1};
     float* d_user_heads[3] = {nullptr, nullptr, nullptr};
     unsigned long long* d_cand_keys = nullptr;
+    unsigned long long *d_bucket_keys = nullptr, *d_sorted_keys = nullptr, *d_win_keys = nullptr;   // NMS workspace (decode_nms.cuh)
+    int *d_seg_start = nullptr, *d_nwin = nullptr;
     int* d_cand_count = nullptr;
     float4* d_boxes = nullptr;
     float* d_out_boxes = nullptr; float* d_out_scores = nullptr; float* d_out_classes = nullptr;
@@ -461,8 +464,12 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
     n.N = e->N; n.nc = nc; n.max_boxes = e->cfg.max_boxes; n.iou_thr = iou_thr;
     n.out_boxes = e->d_out_boxes; n.out_scores = e->d_out_scores; n.out_classes = e->d_out_classes;
     n.out_valid = e->d_out_valid; n.out_idx = e->d_out_idx; n.overflow = e->d_overflow;
-    nms_kernel<<<batch, kNmsThreads, kNmsSmemBytes, e->stream>>>(n);
-    e->launches += 2;
+    n.bucket_keys = e->d_bucket_keys; n.sorted_keys = e->d_sorted_keys; n.seg_start = e->d_seg_start;
+    n.win_keys = e->d_win_keys; n.nwin = e->d_nwin;
+    nms_bucket_kernel<<<batch, kBucketThreads, 0, e->stream>>>(n);
+    nms_class_kernel<<<batch * nc, kClassThreads, 0, e->stream>>>(n);
+    nms_merge_kernel<<<batch, kMergeThreads, kMergeSmemBytes, e->stream>>>(n);
+    e->launches += 4;
     CUDA_TRY(e, cudaGetLastError());
     return Y4_OK;
 }
@@ -633,6 +640,11 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         CREATE_TRY(cudaMalloc(&e->d_user_heads[i], sizeof(float) * B * e->g[i] * e->g[i] * 3 * (5 + cfg->num_classes)));
     CREATE_TRY(cudaMalloc(&e->d_cand_keys, sizeof(unsigned long long) * kCandCap * B));
     CREATE_TRY(cudaMalloc(&e->d_cand_count, sizeof(int) * B));
+    CREATE_TRY(cudaMalloc(&e->d_bucket_keys, sizeof(unsigned long long) * kCandCap * B));
+    CREATE_TRY(cudaMalloc(&e->d_sorted_keys, sizeof(unsigned long long) * kCandCap * B));
+    CREATE_TRY(cudaMalloc(&e->d_win_keys, sizeof(unsigned long long) * (size_t)cfg->num_classes * mb * B));
+    CREATE_TRY(cudaMalloc(&e->d_seg_start, sizeof(int) * 257 * B));
+    CREATE_TRY(cudaMalloc(&e->d_nwin, sizeof(int) * 256 * B));
     CREATE_TRY(cudaMalloc(&e->d_boxes, sizeof(float4) * e->N * B));
     CREATE_TRY(cudaMemset(e->d_boxes, 0, sizeof(float4) * e->N * B));
     CREATE_TRY(cudaMalloc(&e->d_out_boxes, sizeof(float) * 4 * mb * B));
@@ -644,7 +656,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     CREATE_TRY(cudaMemset(e->d_overflow, 0, sizeof(int)));
     e->flush_elems = (size_t)(192u << 20) / sizeof(float4);      // 192 MB > 126 MB L2
     CREATE_TRY(cudaMalloc(&e->d_flush, e->flush_elems * sizeof(float4)));
-    CREATE_TRY(cudaFuncSetAttribute(nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kNmsSmemBytes));
+    CREATE_TRY(cudaFuncSetAttribute(nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeSmemBytes));
     // tcgen05 plans (tensor maps need the buffer addresses, which are now fixed)
     if (cfg->precision == Y4_PREC_FP16 || cfg->precision == Y4_PREC_FP16X3) {
         const bool split = cfg->precision == Y4_PREC_FP16X3;
@@ -672,44 +684,94 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             int kind = tc_plan(d, &c.tc, &terr);
             if (kind < 0) return bail(fail(e, Y4_ERR_CUDA, "tcgen05 plan failed for conv " + std::to_string(c.idx) + ": " + terr));
             c.kind = kind;
-            // Plan-time autotune: the N tile / pipeline depth only change scheduling, never the per-element K-sum
-            // order, so every candidate produces bit-identical outputs.  Time each on the (still zero) buffers.
-            const char* at = getenv("Y4_AUTOTUNE");
-            if (kind > 0 && !(at && at[0] == '0')) {
-                // {N tile, smem budget KB, A-patch reuse, k-blocks per stage}: the budget sets the ring depth and whether one or
-                // two persistent CTAs share an SM.  Each is tried with both epilogues (per-thread stores / slab + TMA store).
-                // Every candidate accumulates K in the same order and rounds once, so outputs are bit-identical across them.
-                const int cand[][4] = {{64, 99, 0, 1}, {64, 200, 0, 1}, {128, 99, 0, 1}, {128, 150, 0, 1}, {128, 200, 0, 1},
-                                       {256, 150, 0, 1}, {256, 200, 0, 1},
-                                       {64, 99, 0, 2}, {64, 205, 0, 3}, {64, 205, 0, 99}, {128, 205, 0, 2}, {128, 205, 0, 3},
-                                       {128, 205, 0, 99}, {256, 205, 0, 2},
-                                       {64, 205, 1, 1}, {128, 205, 1, 1}, {256, 205, 1, 1}, {128, 110, 1, 1}};     // last four: A-patch reuse
-                float best_ms = 1e30f;
-                TcConvPlan best = c.tc;
-                static const bool allow_patch = !(getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '0');
-                static const int epi_mode = getenv("Y4_EPI") ? atoi(getenv("Y4_EPI")) : 1;     // 0 never, 1 autotune, 2 wherever eligible
-                bool have_epi = false;
-                for (int epi = 1; epi >= 0; epi--) {
+            c.desc = d;
+        }
+        // Plan-time autotune, IN CONTEXT: every candidate configuration is planned for all layers it applies to, the whole
+        // forward runs with per-layer CUDA events, and each layer keeps the plan that was fastest where it actually sits
+        // (inputs in L2 or not, neighbours' tails) -- timing a layer alone on a hot L2 picked plans that lose in the pipeline.
+        // Candidates: N tile x shared-memory budget (ring depth; ~110 KB lets two persistent CTAs share an SM) x k-blocks per
+        // barrier x {A-patch reuse, resident weights} x epilogue {per-thread stores, slab + TMA store with 4 or 8 warps}.
+        // Every candidate accumulates K in the same order and rounds once, so outputs are bit-identical across them
+        // (and therefore across GPUs, whatever each one picks).
+        struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw; };
+        std::vector<Cand> cands;
+        const bool allow_patch = !(getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '0');
+        const bool allow_bres = !(getenv("Y4_BRES") && getenv("Y4_BRES")[0] == '0');
+        const int epi_mode = getenv("Y4_EPI") ? atoi(getenv("Y4_EPI")) : 1;     // 0 never, 1 autotune, 2 wherever eligible
+        const int nepi_mode = getenv("Y4_NEPI") ? atoi(getenv("Y4_NEPI")) : 0;  // 4 / 8: only that many epilogue warps
+        const int gw_mode = getenv("Y4_GW") ? atoi(getenv("Y4_GW")) : 0;        // 32 / 64: only that slab group width
+        if (const char* f = getenv("Y4_FORCE")) {                                 // "bn,kb,patch,group,epi,nepi,bres,gw": that plan wherever it applies
+            Cand cd{}; if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d,%d", &cd.bn, &cd.kb, &cd.patch, &cd.group, &cd.epi, &cd.nepi, &cd.bres, &cd.gw) == 8) cands.push_back(cd);
+        } else {
+            // {epilogue, epilogue warps, group width}
+            const int epis[][3] = {{1, 4, 64}, {1, 4, 32}, {1, 8, 32}, {0, 4, 32}};
+            for (int bn : {64, 128, 256})
+                for (auto& ep : epis) {
+                    const int epi = ep[0], nepi = ep[1], gw = ep[2];
                     if (epi && epi_mode == 0) continue;
-                    if (!epi && epi_mode == 2 && have_epi) continue;
-                    for (auto& cd : cand) {
-                        if (cd[2] && !allow_patch) continue;
-                        TcConvPlan trial;
-                        std::string er2;
-                        if (tc_plan(d, &trial, &er2, cd[0], cd[1], cd[2], cd[3], epi) != kind) continue;
-                        if (tc_launch(trial, B, e->stream) != 0) { cudaGetLastError(); continue; }      // warm-up + smem attribute
-                        cudaEventRecord(e->ev0, e->stream);
-                        for (int rep = 0; rep < 3; rep++) tc_launch(trial, B, e->stream);
-                        cudaEventRecord(e->ev1, e->stream);
-                        if (cudaEventSynchronize(e->ev1) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, "autotune launch failed for conv " + std::to_string(c.idx)));
-                        float ms = 0.f;
-                        cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-                        if (epi) have_epi = true;
-                        if (ms < best_ms) { best_ms = ms; best = trial; }
+                    if (epi && nepi_mode && nepi != nepi_mode) continue;
+                    if (epi && gw_mode && gw != gw_mode) continue;
+                    for (int bres = 0; bres <= (allow_bres ? 1 : 0); bres++) {
+                        for (int g : {1, 2}) cands.push_back({bn, 112, 0, g, epi, nepi, bres, gw});       // two CTAs per SM
+                        for (int g : {1, 2, 3, 99}) cands.push_back({bn, 224, 0, g, epi, nepi, bres, gw});
+                        if (!bres) cands.push_back({bn, 150, 0, 1, epi, nepi, 0, gw});
                     }
+                    if (allow_patch) { cands.push_back({bn, 224, 1, 1, epi, nepi, 0, gw}); cands.push_back({bn, 112, 1, 1, epi, nepi, 0, gw}); }
                 }
-                c.tc = best;
+        }
+        const char* at = getenv("Y4_AUTOTUNE");
+        if (!(at && at[0] == '0')) {
+            const size_t nsteps = e->steps.size();
+            std::vector<cudaEvent_t> ev(nsteps + 1);
+            for (auto& x : ev) cudaEventCreate(&x);
+            std::vector<float> best_ms(e->convs.size(), 1e30f);
+            std::vector<TcConvPlan> best(e->convs.size()), trial(e->convs.size());
+            std::vector<char> has(e->convs.size());
+            const bool forced = getenv("Y4_FORCE") != nullptr;
+            for (int ci = -1; ci < (int)cands.size(); ci++) {                      // -1: the default plans
+                bool any = ci < 0;
+                for (size_t li = 0; li < e->convs.size(); li++) {
+                    ConvOp& c = e->convs[li];
+                    has[li] = 0;
+                    if (c.kind != 1 && c.kind != 2) continue;
+                    if (ci < 0) { trial[li] = c.tc; best[li] = c.tc; has[li] = 1; continue; }
+                    const Cand& cd = cands[ci];
+                    if (!cd.epi && epi_mode == 2 && best[li].p.epi) continue;
+                    std::string er2;
+                    if (tc_plan(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw) != c.kind) continue;
+                    has[li] = 1; any = true;
+                }
+                if (!any) continue;
+                float t_min[2] = {0, 0};
+                std::vector<float> ms(nsteps, 1e30f);
+                for (int rep = 0; rep < 3; rep++) {                               // rep 0 warms up (and sets the smem attribute)
+                    cudaEventRecord(ev[0], e->stream);
+                    for (size_t i = 0; i < nsteps; i++) {
+                        auto& st = e->steps[i];
+                        if (st.type == 0) {
+                            ConvOp& c = e->convs[st.conv];
+                            const TcConvPlan keep = c.tc;
+                            if (has[st.conv]) c.tc = trial[st.conv]; else if (c.kind == 1 || c.kind == 2) c.tc = best[st.conv];
+                            const int rc2 = run_conv(e, c, B);
+                            c.tc = keep;
+                            if (rc2) { cudaGetLastError(); if (has[st.conv]) has[st.conv] = 2; }        // 2: launch refused
+                        } else launch_spp(e, B);
+                        cudaEventRecord(ev[i + 1], e->stream);
+                    }
+                    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, "autotune forward failed (candidate " + std::to_string(ci) + ")"));
+                    if (rep == 0) continue;
+                    for (size_t i = 0; i < nsteps; i++) { float t = 0.f; cudaEventElapsedTime(&t, ev[i], ev[i + 1]); if (t < ms[i]) ms[i] = t; }
+                }
+                (void)t_min;
+                for (size_t i = 0; i < nsteps; i++) {
+                    if (e->steps[i].type != 0) continue;
+                    const int li = e->steps[i].conv;
+                    if (has[li] != 1) continue;
+                    if (ms[i] < best_ms[li] || (forced && ci >= 0)) { best_ms[li] = ms[i]; best[li] = trial[li]; }
+                }
             }
+            for (size_t li = 0; li < e->convs.size(); li++) if (e->convs[li].kind == 1 || e->convs[li].kind == 2) e->convs[li].tc = best[li];
+            for (auto& x : ev) cudaEventDestroy(x);
         }
         // autotune launches wrote act(bias=0)=0-ish garbage into interiors only; halos were never touched.
     }
@@ -731,6 +793,7 @@ void y4_destroy(y4_engine* e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 3; i++) cudaFree(e->d_user_heads[i]);
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
+    cudaFree(e->d_bucket_keys); cudaFree(e->d_sorted_keys); cudaFree(e->d_win_keys); cudaFree(e->d_seg_start); cudaFree(e->d_nwin);
     cudaFree(e->d_out_boxes); cudaFree(e->d_out_scores); cudaFree(e->d_out_classes);
     cudaFree(e->d_out_valid); cudaFree(e->d_out_idx); cudaFree(e->d_overflow);
     cudaFree(e->d_flush); cudaFree(e->d_gather);
@@ -1021,8 +1084,9 @@ int y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info) {
     info->flops = 2ll * c.N_OH * c.N_OH * c.cout * c.K;
     snprintf(info->out_name, sizeof(info->out_name), "%s", c.out_name.c_str());
     const bool tc = c.kind == 1 || c.kind == 2;
-    info->tc_mode = tc ? c.tc.p.mode : 0; info->tc_epilogue = tc ? c.tc.p.epi : 0; info->tc_stages = tc ? c.tc.stages : 0;
+    info->tc_mode = tc ? c.tc.p.mode : 0; info->tc_epilogue = tc && c.tc.p.epi ? c.tc.p.epi_gw : 0; info->tc_stages = tc ? c.tc.stages : 0;
     info->tc_group = tc ? c.tc.p.group : 0; info->tc_ctas_per_sm = tc ? c.tc.ctas_per_sm : 0; info->tc_bk = tc ? c.tc.bk : 0;
+    info->tc_epi_warps = tc ? c.tc.nepi : 0; info->tc_resident_w = tc ? c.tc.p.bres : 0;
     return Y4_OK;
 }
 
