@@ -57,6 +57,7 @@ struct TcParams {
     int num_tiles, n_tiles, bias_n;   // tiles = m_tiles * n_tiles (n fastest); bias_n floats staged in smem
     // mode 3 (3x3 stride 1, A-patch reuse): one (128 + 2*Wp + 2)-row patch per 64-channel block feeds all 9 taps
     int patch_boxes, patch_bytes, patch_slots, base_off_mode;
+    int patch_taps, patch_box_rows;      // 9: one patch holds the whole 3x3 halo; 3: one patch per kernel row (rows m0 + (kh-1)*Wp - 1 ..), fed to its 3 kw taps
     int mode;                    // 1 flat, 2 box
     int epi;                     // 0: per-thread global stores; 1: swizzled smem slab per warp -> TMA store (flat modes, fp16 out)
     int bres;                    // 1: the whole weight matrix is loaded once per CTA and stays in shared memory (n_tiles == 1)
@@ -74,6 +75,7 @@ struct TcConvPlan {
     TcParams p;
     int kind = 0;                // 1 flat, 2 box
     int tile_n = 0, bk = 64, stages = 0, ctas_per_sm = 1, nepi = 4;
+    int cta2 = 0;                // 1: CTA-pair kernel (conv_tc2.cuh), 256-row tiles, tcgen05.mma.cta_group::2
     size_t smem = 0;
     int in_Hp = 0, in_Wp = 0;
 };
@@ -496,16 +498,18 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : 2) conv_tc_kernel(
     const uint32_t wres_bytes = p.bres ? (uint32_t)p.num_kb * (uint32_t)B_BYTES : 0u;
     const uint32_t ASTRIDE = p.bres ? (uint32_t)A_BYTES : SBYTES;                 // bytes per k-block slot of the ring
     const uint32_t ring0 = base + wres_bytes;                                       // first ring stage (modes 1,2)
-    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes + S * B_BYTES) : wres_bytes + (uint32_t)(S * G) * ASTRIDE;
-    const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);      // mode 3: first B stage
+    const uint32_t ring_bytes = p.mode == 3 ? (uint32_t)(p.patch_slots * p.patch_bytes) + (p.bres ? wres_bytes : (uint32_t)(S * B_BYTES))
+                                            : wres_bytes + (uint32_t)(S * G) * ASTRIDE;
+    const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);      // mode 3: first B stage, or the resident W
+    const uint32_t wres = p.mode == 3 ? bring : base;                              // resident W blocks, in K order
     const uint32_t epi_bytes = (!SPLIT && p.epi) ? epi_slab_bytes(NEPI, p.epi_gw) : 0u;   // 1024 B aligned: ring_bytes is a multiple of 1024
     const uint32_t slabs = base + ring_bytes;
     const uint32_t bars = slabs + epi_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
     const uint32_t tmem_slot = bars + 16u * S + 32u;
-    const uint32_t bar_pfull = bars + 16u * S + 48u, bar_pempty = bars + 16u * S + 80u;
-    const uint32_t bar_w = bar_pfull + 24u;                                         // resident-W barrier (patch slot 3 is never used)
-    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + epi_bytes + 16u * S + 112u);
+    const uint32_t bar_pfull = bars + 16u * S + 48u, bar_pempty = bars + 16u * S + 112u;   // 8 patch slots each
+    const uint32_t bar_w = bars + 16u * S + 176u;                                   // resident-W barrier
+    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + epi_bytes + 16u * S + 192u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     long long* dbg = (p.dbg && blockIdx.x < 4096) ? p.dbg + (size_t)blockIdx.x * 16 : nullptr;
@@ -519,7 +523,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : 2) conv_tc_kernel(
         if (p.mode == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
         for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, NEPI); }
-        for (int a = 0; a < 4; a++) { mbar_init(bar_pfull + 8u * a, 1); mbar_init(bar_pempty + 8u * a, 1); }
+        for (int a = 0; a < 8; a++) { mbar_init(bar_pfull + 8u * a, 1); mbar_init(bar_pempty + 8u * a, 1); }
+        mbar_init(bar_w, 1);
         if (p.mode == 3) tma_prefetch_desc(&p.tmA[1]);
         if (p.epi) tma_prefetch_desc(&p.tmOut);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -545,39 +550,57 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : 2) conv_tc_kernel(
             uint32_t it = 0;
             long long w_empty = 0;
             if (p.mode == 3) {
-                // patches run one (tile, channel-block) pair ahead of the B loads; 3 slots make that wait-free
+                // A patches: one patch feeds patch_taps taps through row-shifted UMMA descriptors.  patch_taps = 9: rows
+                // m0 - Wp - 1 .. cover the whole 3x3 halo (pays when Wp is small); patch_taps = 3: one patch per kernel row kh,
+                // rows m0 + (kh-1)*Wp - 1 .. +130, feeding kw = 0,1,2 (A traffic 3x instead of 9x whatever Wp is).
+                // Patches run up to patch_slots - 1 ahead of the B loads.
                 const int ncb = p.kb_per_tap;
+                const int PT = p.patch_taps, ppc = 9 / PT;
                 const int my_tiles = ((int)p.num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-                const int pairs = my_tiles * ncb;
+                const int npatch = my_tiles * ncb * ppc;
                 const uint32_t PS = (uint32_t)p.patch_slots;
+                const uint32_t ptx = (uint32_t)p.patch_boxes * (uint32_t)p.patch_box_rows * (uint32_t)SWZ;
+                if (p.bres) {
+                    mbar_expect_tx(bar_w, (uint32_t)p.num_kb * (uint32_t)B_BYTES);
+                    for (int kb = 0; kb < p.num_kb; kb++) {
+                        const int cb = kb / 9, tap = kb - cb * 9;
+                        tma_load_2d(wres + (uint32_t)kb * (uint32_t)B_BYTES, &p.tmW, bar_w, (tap * ncb + cb) * BK, 0);
+                    }
+                }
                 uint32_t pit = 0;
                 auto issue_patch = [&](int j) {
-                    const int tile = (int)blockIdx.x + (j / ncb) * (int)gridDim.x;
-                    const int cb = j - (j / ncb) * ncb;
-                    const TileCoord tc = decode_tile<BN>(p, tile);
+                    const int tl = j / (ncb * ppc);
+                    const int rem = j - tl * (ncb * ppc);
+                    const int cb = rem / ppc, g = rem - cb * ppc;
+                    const TileCoord tc = decode_tile<BN>(p, (int)blockIdx.x + tl * (int)gridDim.x);
                     const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
                     mbar_wait(bar_pempty + 8u * ps, pph ^ 1u);
                     const uint32_t fb = bar_pfull + 8u * ps;
-                    mbar_expect_tx(fb, (uint32_t)p.patch_boxes * 32u * (uint32_t)SWZ);
+                    mbar_expect_tx(fb, ptx);
                     const uint32_t dst = base + ps * (uint32_t)p.patch_bytes;
-                    const int row0 = (int)tc.m0 - p.Wp - 1;
+                    const int row0 = (int)tc.m0 - 1 + (PT == 9 ? -p.Wp : (g - 1) * p.Wp);
                     for (int b = 0; b < p.patch_boxes; b++)
-                        tma_load_2d(dst + (uint32_t)b * 32u * (uint32_t)SWZ, &p.tmA[1], fb, cb * BK, row0 + b * 32);
+                        tma_load_2d(dst + (uint32_t)(b * p.patch_box_rows) * (uint32_t)SWZ, &p.tmA[1], fb, cb * BK, row0 + b * p.patch_box_rows);
                     pit++;
                 };
-                if (pairs > 0) issue_patch(0);
-                for (int j = 0; j < pairs; j++) {
-                    if (j + 1 < pairs) issue_patch(j + 1);
-                    const int tile = (int)blockIdx.x + (j / ncb) * (int)gridDim.x;
-                    const int cb = j - (j / ncb) * ncb;
+                int issued = 0;
+                const int ahead = (int)PS > 2 ? (int)PS - 2 : 1;      // issuing patch j + ahead needs patch j + ahead - PS consumed: keep that behind the B loads
+                for (int j = 0; j < npatch; j++) {
+                    while (issued < npatch && issued <= j + ahead) issue_patch(issued++);
+                    if (j == 0) Y4_STAMP(2);
+                    if (p.bres) continue;
+                    const int tl = j / (ncb * ppc);
+                    const int rem = j - tl * (ncb * ppc);
+                    const int cb = rem / ppc, g = rem - cb * ppc;
+                    const int tile = (int)blockIdx.x + tl * (int)gridDim.x;
                     const int n0 = (tile % p.n_tiles) * BN;
-                    for (int tap = 0; tap < 9; tap++, it++) {
+                    for (int t = 0; t < PT; t++, it++) {
+                        const int tap = g * PT + t;
                         const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
                         mbar_wait_t(bar_empty + 8u * s, ph ^ 1u, dbg ? &w_empty : nullptr);
                         const uint32_t fb = bar_full + 8u * s;
                         mbar_expect_tx(fb, (uint32_t)B_BYTES);
                         tma_load_2d(bring + s * (uint32_t)B_BYTES, &p.tmW, fb, (tap * ncb + cb) * BK, n0);
-                        if (it == 0) Y4_STAMP(2);
                     }
                     if (j == 0) Y4_STAMP(3);
                 }
@@ -656,26 +679,35 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : 2) conv_tc_kernel(
                 const uint32_t tacc = tmem_base + as * (uint32_t)BN;
                 if (p.mode == 3) {
                     const uint32_t PS = (uint32_t)p.patch_slots;
-                    for (int cb = 0; cb < p.kb_per_tap; cb++, pit++) {
+                    const int PT = p.patch_taps, ppc = 9 / PT;
+                    for (int cb = 0; cb < p.kb_per_tap; cb++)
+                    for (int g = 0; g < ppc; g++, pit++) {
                         const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
                         mbar_wait_t(bar_pfull + 8u * ps, pph, dbg ? &w_pfull : nullptr);
                         tc_fence_after();
                         const uint32_t pa = base + ps * (uint32_t)p.patch_bytes;
-                        for (int tap = 0; tap < 9; tap++, it++) {
-                            const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
-                            mbar_wait_t(bar_full + 8u * s, ph, dbg ? &w_full : nullptr);
-                            tc_fence_after();
-                            if (it == 0) Y4_STAMP(4);
-                            const int kh = tap / 3, kw = tap - kh * 3;
-                            // patch row 0 is output row m0 shifted by -(Wp+1): tap (kh,kw) starts at row kh*Wp + kw
-                            const uint64_t da = make_smem_desc_bo<SWZ>(pa + (uint32_t)(kh * p.Wp + kw) * (uint32_t)SWZ, p.base_off_mode);
-                            const uint64_t db = make_smem_desc<SWZ>(bring + s * (uint32_t)B_BYTES);
+                        for (int t = 0; t < PT; t++) {
+                            const int tap = g * PT + t;
+                            uint32_t bsm;
+                            if (p.bres) bsm = wres + (uint32_t)(cb * 9 + tap) * (uint32_t)B_BYTES;
+                            else {
+                                const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                                mbar_wait_t(bar_full + 8u * s, ph, dbg ? &w_full : nullptr);
+                                tc_fence_after();
+                                bsm = bring + s * (uint32_t)B_BYTES;
+                            }
+                            if (cb == 0 && tap == 0 && ti == 0) Y4_STAMP(4);
+                            // full patch: row 0 is output row m0 shifted by -(Wp+1), tap (kh,kw) starts at row kh*Wp + kw;
+                            // row patch: row 0 is m0 + (kh-1)*Wp - 1, tap kw starts at row kw
+                            const int roff = PT == 9 ? (tap / 3) * p.Wp + (tap % 3) : t;
+                            const uint64_t da = make_smem_desc_bo<SWZ>(pa + (uint32_t)roff * (uint32_t)SWZ, p.base_off_mode);
+                            const uint64_t db = make_smem_desc<SWZ>(bsm);
 #pragma unroll
                             for (int k = 0; k < BK / 16; k++)
                                 umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (cb | tap | k) ? 1u : 0u);
-                            umma_commit(bar_empty + 8u * s);
+                            if (!p.bres) { umma_commit(bar_empty + 8u * (it % (uint32_t)S)); it++; }
                         }
-                        umma_commit(bar_pempty + 8u * ps);      // all 9 taps have read this patch
+                        umma_commit(bar_pempty + 8u * ps);      // all taps of this patch have been read
                     }
                 } else
                 for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
@@ -1031,31 +1063,32 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     }
     size_t wres_bytes = 0;
     if (bres) {
-        // resident weights: one N tile, no split planes, not the patch mode (whose ring holds B tiles)
+        // resident weights: one N tile, no split planes
         wres_bytes = (size_t)bn * K * 2;
-        if (d.cout_pad != bn || d.split || patch || wres_bytes > 96 * 1024) return 0;
+        if (d.cout_pad != bn || d.split || wres_bytes > 96 * 1024) return 0;
         p.bres = 1;
     }
     size_t stage_bytes = bres ? (size_t)128 * bk * 2 : ((size_t)128 * bk * 2 + (size_t)bn * bk * 2) * (d.split ? 2 : 1);
     size_t ring_fixed = wres_bytes;
-    if (!patch && getenv("Y4_FORCE_PATCH") && P.kind == 1 && d.k == 3 && bk == 64 && !bres) { patch = 1; if (smem_budget_kb < 200) smem_budget_kb = 200; }
+    if (!patch && getenv("Y4_FORCE_PATCH") && P.kind == 1 && d.k == 3) { patch = atoi(getenv("Y4_FORCE_PATCH")); if (smem_budget_kb < 200) smem_budget_kb = 200; }
+    size_t patch_bytes = 0;
     if (patch) {
-        // A-patch reuse (mode 3): 3x3 stride 1, 64-channel blocks; patch = 130 + 2*Wp rows, loaded as 32-row TMA boxes
-        if (P.kind != 1 || d.k != 3 || bk != 64) return 0;
-        const int prow = 130 + 2 * in_Wp;
-        p.patch_boxes = (prow + 31) / 32;
-        p.patch_bytes = ((p.patch_boxes * 32 * swz + 1023) / 1024) * 1024;
-        p.patch_slots = 3;
+        // A-patch reuse (mode 3): 3x3 stride 1.  patch = 1: one patch of 130 + 2*Wp rows (32-row TMA boxes) feeds all 9 taps;
+        // patch = 3: one 136-row box per kernel row feeds its 3 kw taps
+        if (P.kind != 1 || d.k != 3 || d.split || (patch != 1 && patch != 3)) return 0;
+        if (patch == 1) { p.patch_taps = 9; p.patch_box_rows = 32; p.patch_boxes = (130 + 2 * in_Wp + 31) / 32; }
+        else { p.patch_taps = 3; p.patch_box_rows = 136; p.patch_boxes = 1; }
+        p.patch_bytes = ((p.patch_boxes * p.patch_box_rows * swz + 1023) / 1024) * 1024;
+        patch_bytes = (size_t)p.patch_bytes;
         p.mode = 3;
         p.base_off_mode = 0;   // measured on B200: the MMA derives the swizzle phase from absolute smem address bits;
                                // a non-zero 'matrix base offset' double-counts it (tests/test_gpu_tc.py with Y4_BASE_OFFSET=1 fails)
         if (const char* env = getenv("Y4_BASE_OFFSET")) p.base_off_mode = atoi(env);
         cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)d.max_batch * in_Hp * in_Wp};
         cuuint64_t str[1] = {(cuuint64_t)d.in_ld * 2};
-        cuuint32_t box[2] = {(cuuint32_t)bk, 32};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.patch_box_rows};
         if (!encode_map(&p.tmA[1], in_base, 2, dims, str, box, swz, err)) return -1;
-        ring_fixed = (size_t)p.patch_slots * p.patch_bytes;
-        stage_bytes = (size_t)bn * bk * 2;                            // the ring holds B tiles only
+        stage_bytes = (size_t)bn * bk * 2;                            // the ring holds B tiles only (none with resident W)
     }
     if (patch || group < 1) group = 1;
     if (group > p.num_kb) group = p.num_kb;
@@ -1064,15 +1097,28 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     // the ring runs across tile boundaries (persistent CTA), so it may be deeper than one tile's k-blocks: for the K = 64
     // layers that is what keeps several tiles of activations in flight
     // smem_budget_kb bounds the CTA's TOTAL dynamic shared memory (112 KB: two CTAs per SM, 224 KB: one)
-    const size_t fixed = 1024 + ring_fixed + epi_bytes + 16 * 8 + 112 + 8 * (size_t)d.cout_pad;
+    const size_t fixed = 1024 + ring_fixed + epi_bytes + 16 * 8 + 192 + 8 * (size_t)d.cout_pad;
     const size_t budget = (size_t)smem_budget_kb * 1024;
-    int S = budget > fixed ? (int)((budget - fixed) / stage_bytes) : 0;
-    if (S > 8) S = 8;
-    if (S < 2) { if (group > 1 || patch || bres || epi) return 0; S = 2; }      // plain plans always get a double buffer
+    int S;
+    if (patch) {
+        // B ring first (3-4 stages are enough: a B tile is re-fetched from L2 for every tap), the rest goes to patch slots
+        S = bres ? 2 : (patch == 1 ? 3 : 4);                          // (bres: the ring is unused, S only sizes the barrier arrays)
+        const size_t bpart = bres ? 0 : (size_t)S * stage_bytes;
+        if (budget < fixed + bpart + 3 * patch_bytes) return 0;
+        int PS = (int)((budget - fixed - bpart) / patch_bytes);
+        const int want = patch == 1 ? 3 : 8;
+        p.patch_slots = PS > want ? want : PS;
+        ring_fixed += (size_t)p.patch_slots * patch_bytes;
+        if (bres) stage_bytes = 0;
+    } else {
+        S = budget > fixed ? (int)((budget - fixed) / stage_bytes) : 0;
+        if (S > 8) S = 8;
+        if (S < 2) { if (group > 1 || bres || epi) return 0; S = 2; }      // plain plans always get a double buffer
+    }
     P.stages = S; p.stages = S;
     p.n_tiles = (p.cout_store + bn - 1) / bn;
     p.bias_n = d.cout_pad;
-    P.smem = 1024 + ring_fixed + S * stage_bytes + epi_bytes + 16 * S + 112 + 8 * (size_t)p.bias_n;   // bias + weight-scale arrays
+    P.smem = 1024 + ring_fixed + S * stage_bytes + epi_bytes + 16 * S + 192 + 8 * (size_t)p.bias_n;   // bias + weight-scale arrays
     if (P.smem > 225 * 1024) { *err = "smem budget exceeded"; return -1; }
     int cps = (int)((227 * 1024) / (P.smem + 1024));            // +1 KB: per-CTA reserved shared memory
     const int tmem_cols = 2 * bn;

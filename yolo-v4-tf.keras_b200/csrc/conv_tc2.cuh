@@ -1,0 +1,352 @@
+// cta_group::2 variant of the flat tcgen05 conv kernel (conv_tc.cuh): a cluster of two CTAs on an SM pair computes a
+// 256-row x BN tile with ONE tcgen05.mma.cta_group::2 per K step.
+//
+// Why: with SS operands a 128 x N x 16 MMA reads its A (4 KB) and B (N * 32 B) slices from shared memory for every
+// instruction.  At N = 128 that is 8 KB per 64 tensor cycles = the whole 128 B/clk shared-memory port, before the TMA has
+// written a byte; at N = 256 it is 96 B/clk, and the TMA writes as much again (measured: 45 % / 60 % tensor-pipe active,
+// MMA thread waiting on data 17-20 %).  In a CTA pair each CTA stages its own 128 rows of A and only HALF of the B tile
+// (BN/2 weight rows); the hardware feeds both halves to both tensor cores, so B traffic per SM (L2 -> smem and
+// smem -> tensor core) halves.
+//
+// Roles per CTA as in conv_tc.cuh (warp 0 TMA producer, warp 1 MMA / TMEM alloc, warps 2.. epilogue), except:
+//   * every TMA load names the LEADER's (cluster rank 0) full barrier: one barrier completes when both CTAs' bytes landed;
+//   * only the leader issues MMAs; tcgen05.commit multicasts the arrive to both CTAs' empty / tfull barriers;
+//   * the peer's epilogue warps arrive remotely on the leader's tempty barrier (mbarrier.arrive.shared::cluster);
+//   * TMEM is allocated with cta_group::2 by warp 1 of both CTAs; cluster barriers fence start-up and tear-down.
+// Flat mode (1x1 and 3x3 stride 1), 64-channel K blocks, fp16 in / fp16 out through the slab epilogue only.
+#pragma once
+#include "conv_tc.cuh"
+
+namespace y4 {
+
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;              // shared::cluster address of the same offset in the even CTA of the pair
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_cg2(uint32_t dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrive on the barrier at this smem offset in BOTH CTAs once all previously issued MMAs have completed
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {       // from either CTA of the pair
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+
+template <int BN, int NEPI>
+__global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __grid_constant__ TcParams p) {
+    constexpr int BK = 64, SWZ = 128;
+    constexpr int A_BYTES = 128 * BK * 2;
+    constexpr int B_BYTES = (BN / 2) * BK * 2;              // this CTA's half of the weight tile
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;                  // two accumulator stages
+    constexpr uint32_t IDESC = make_idesc(256, BN);
+
+    extern __shared__ unsigned char tc_smem[];
+    const uint32_t raw = smem_u32(tc_smem);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const int S = p.stages, G = p.group;
+    const uint32_t ring_bytes = (uint32_t)(S * G) * (uint32_t)STAGE_BYTES;
+    const uint32_t epi_bytes = epi_slab_bytes(NEPI, p.epi_gw);
+    const uint32_t slabs = base + ring_bytes;
+    const uint32_t bars = slabs + epi_bytes;
+    const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
+    const uint32_t tmem_slot = bars + 16u * S + 32u;
+    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + epi_bytes + 16u * S + 192u);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = (int)(blockIdx.x >> 1), nclusters = (int)(gridDim.x >> 1);
+    pdl_launch_dependents();
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmW);
+        tma_prefetch_desc(&p.tmA[0]);
+        tma_prefetch_desc(&p.tmOut);
+        for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
+        for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 2 * NEPI); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) tmem_alloc_cg2(tmem_slot, TMEM_COLS);
+    const float bmul = p.act == 2 ? 1.4426950408889634f : 1.0f;          // mish layers keep b * log2(e) (act_fast)
+    if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 32 * NEPI) sbias[i] = p.bias[i] * bmul;
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                     // the peer's barriers exist before anything is signalled across the pair
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+    pdl_wait();
+
+    // cluster tile ct -> (256-row block, N tile); this CTA: rows +128*rank, weight rows +BN/2*rank
+    auto tile_m0 = [&](int ct) { return (long long)(ct / p.n_tiles) * 256 + 128 * (long long)rank; };
+    auto tile_n0 = [&](int ct) { return (ct % p.n_tiles) * BN; };
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters) {
+                const long long m0 = tile_m0(ct);
+                const int n0 = tile_n0(ct);
+                for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
+                    const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    const uint32_t fb = (bar_full + 8u * s) & kPeerBitMask;          // the leader's barrier collects both CTAs' bytes
+                    const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
+                    if (rank == 0) mbar_expect_tx(bar_full + 8u * s, 2u * (uint32_t)gcount * (uint32_t)STAGE_BYTES);
+                    for (int kk = 0; kk < gcount; kk++) {
+                        const int kb = kb0 + kk;
+                        int tap = 0, cb = kb;
+                        if (p.ksize == 3) { cb = kb / 9; tap = kb - cb * 9; }        // channel block outer, tap inner (as conv_tc.cuh)
+                        int shift = 0;
+                        if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
+                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * (uint32_t)STAGE_BYTES;
+                        tma_load_2d_cg2(sa, &p.tmA[0], fb, cb * BK, (int)(m0 + shift));
+                        tma_load_2d_cg2(sa + A_BYTES, &p.tmW, fb, (tap * p.kb_per_tap + cb) * BK, n0 + (int)rank * (BN / 2));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            uint32_t it = 0, ti = 0;
+            for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters, ti++) {
+                const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+                mbar_wait(bar_tempty + 8u * as, aph ^ 1u);                           // both CTAs' epilogues have drained this stage
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + as * (uint32_t)BN;
+                for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
+                    const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                    mbar_wait(bar_full + 8u * s, ph);
+                    tc_fence_after();
+                    const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
+                    for (int kk = 0; kk < gcount; kk++) {
+                        const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * (uint32_t)STAGE_BYTES;
+                        const uint64_t da = make_smem_desc<SWZ>(sa);
+                        const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++)
+                            umma_f16_cg2(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
+                    }
+                    umma_commit_cg2(bar_empty + 8u * s);
+                }
+                umma_commit_cg2(bar_tfull + 8u * as);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int set = (warp - 2) >> 2;
+        constexpr int NSETS = NEPI / 4;
+        constexpr int NCH = BN / 32;
+        const int r = q * 32 + lane;
+        uint32_t ti = 0, sit = 0;
+        const bool has_res = p.res != nullptr;
+        const bool gw64 = p.epi_gw == 64;
+        const uint32_t slab_bytes = gw64 ? 2u * kSlabBytes : kSlabBytes;
+        const uint32_t my_slabs = slabs + (uint32_t)(warp - 2) * 2u * slab_bytes;
+        if (has_res && cluster_id < p.num_tiles)
+            res_prefetch(p, my_slabs, tile_m0(cluster_id) + q * 32, tile_n0(cluster_id) + 32 * set, lane, gw64);
+        for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters, ti++) {
+            const long long m0 = tile_m0(ct);
+            const int n0 = tile_n0(ct);
+            const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
+            const long long pr = m0 + r;
+            bool valid = pr < p.M_total;
+            {
+                const unsigned up = (unsigned)(valid ? pr : 0);
+                const int wp = (int)(up % (unsigned)p.Wp);
+                const int hp = (int)((up / (unsigned)p.Wp) % (unsigned)p.Hp);
+                valid = valid && hp >= 1 && hp <= p.Hp - 2 && wp >= 1 && wp <= p.Wp - 2;
+            }
+            mbar_wait(bar_tfull + 8u * as, aph);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN;
+            uint32_t va[32];
+            [[maybe_unused]] uint32_t vb[32];
+            auto do_group = [&](const uint32_t (&v)[32], int k) {
+                if (n0 + 32 * k >= p.cout_store) return;
+                const int h = gw64 ? (k & 1) : 0;
+                const bool last = !gw64 || h == 1 || n0 + 32 * (k + 1) >= p.cout_store;
+                const uint32_t slab = my_slabs + (sit & 1u) * slab_bytes;
+                if (has_res && h == 0) { cp_async_wait_all(); __syncwarp(); }
+                epi_group(p, v, sbias + n0 + 32 * k, slab, lane, h, valid, has_res, gw64);
+                if (!last) return;
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                if (has_res) {
+                    int nk = gw64 ? k + 1 : k + NSETS, nct = ct;
+                    if (nk >= NCH || n0 + 32 * nk >= p.cout_store) { nk = set; nct = ct + nclusters; }
+                    if (nct < p.num_tiles)
+                        res_prefetch(p, my_slabs + ((sit + 1u) & 1u) * slab_bytes, tile_m0(nct) + q * 32, tile_n0(nct) + 32 * nk, lane, gw64);
+                }
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) { tma_store_2d(&p.tmOut, slab, n0 + 32 * (k - h), (int)(m0 + q * 32)); bulk_commit(); }
+                sit++;
+            };
+            auto release_acc = [&]() { tc_fence_before(); if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * as); };
+            if constexpr (NEPI == 8) {
+#pragma unroll 1
+                for (int k = set; k < NCH; k += NSETS) {
+                    tmem_ld32_issue(tacc + (uint32_t)(32 * k), va);
+                    tmem_ld_wait(va);
+                    if (k + NSETS >= NCH) release_acc();
+                    do_group(va, k);
+                    __syncwarp();
+                }
+            } else {
+                tmem_ld32_issue(tacc + (uint32_t)(32 * set), va);
+#pragma unroll 1
+                for (int k = set; k < NCH; k += 2 * NSETS) {
+                    const int k2 = k + NSETS;
+                    tmem_ld_wait(va);
+                    if (k2 < NCH) tmem_ld32_issue(tacc + (uint32_t)(32 * k2), vb); else release_acc();
+                    do_group(va, k);
+                    __syncwarp();
+                    if (k2 < NCH) {
+                        tmem_ld_wait(vb);
+                        if (k2 + NSETS < NCH) tmem_ld32_issue(tacc + (uint32_t)(32 * (k2 + NSETS)), va); else release_acc();
+                        do_group(vb, k2);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        if (lane == 0) bulk_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                     // neither CTA may exit (or free TMEM) while the pair still uses its smem / barriers
+    if (warp == 1) { tc_fence_after(); tmem_dealloc_cg2(tmem_base, TMEM_COLS); }
+}
+
+template <int BN, int NEPI>
+inline cudaError_t launch_tc2(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = dim3(64 + 32 * NEPI); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, conv_tc2_kernel<BN, NEPI>, pl.p);
+}
+
+// launch of a cta2 plan (tc_plan2): one cluster per SM pair
+inline int tc2_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
+    TcConvPlan pl = pl_in;
+    pl.p.M_total = (long long)batch * pl.p.Hp * pl.p.Wp;
+    const long long m_tiles = (pl.p.M_total + 255) / 256;
+    pl.p.num_tiles = (int)(m_tiles * pl.p.n_tiles);
+    const int max_clusters = sm_count() / 2;
+    const int nclusters = pl.p.num_tiles < max_clusters ? pl.p.num_tiles : max_clusters;
+    dim3 grid((unsigned)(2 * nclusters));
+    cudaError_t e = cudaErrorInvalidValue;
+    if (pl.nepi == 8) {
+        switch (pl.tile_n) {
+            case 64: e = launch_tc2<64, 8>(pl, grid, st); break;
+            case 128: e = launch_tc2<128, 8>(pl, grid, st); break;
+            case 256: e = launch_tc2<256, 8>(pl, grid, st); break;
+        }
+    } else {
+        switch (pl.tile_n) {
+            case 64: e = launch_tc2<64, 4>(pl, grid, st); break;
+            case 128: e = launch_tc2<128, 4>(pl, grid, st); break;
+            case 256: e = launch_tc2<256, 4>(pl, grid, st); break;
+        }
+    }
+    return e == cudaSuccess ? 0 : -1;
+}
+
+// Plan for the CTA-pair kernel; returns 1 when the layer is eligible (flat mode, 64-channel K blocks, fp16 slab epilogue).
+inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn, int smem_budget_kb, int group, int nepi, int gw) {
+    if (d.raw_in || d.cin % 64 != 0 || d.stride != 1 || d.split || d.out_f32 || d.upsample) return 0;
+    if (d.cout_pad % bn || d.cout % gw != 0 || (gw != 32 && (gw != 64 || nepi != 4)) || (nepi != 4 && nepi != 8)) return 0;
+    TcConvPlan P;
+    TcParams& p = P.p;
+    memset(&p, 0, sizeof(p));
+    P.tile_n = bn; P.bk = 64; P.kind = 1; P.nepi = nepi; P.cta2 = 1; P.ctas_per_sm = 1;
+    p.mode = 1; p.epi = 1; p.epi_gw = gw;
+    p.bias = d.bias; p.out = d.out; p.res = reinterpret_cast<const __half*>(d.res);
+    p.act_scale = 1.f; p.inv_act_scale = 1.f;
+    p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
+    p.act = d.act;
+    if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);
+    p.cout_store = d.cout;
+    p.ksize = d.k;
+    p.kb_per_tap = d.cin / 64;
+    p.num_kb = d.k * d.k * p.kb_per_tap;
+    const int K = d.k * d.k * d.cin;
+    const int in_Hp = d.in_H + 2, in_Wp = d.in_H + 2;
+    P.in_Hp = in_Hp; P.in_Wp = in_Wp;
+    p.Hp = in_Hp; p.Wp = in_Wp;
+    p.rows_alloc = (long long)d.max_batch * in_Hp * in_Wp;
+    char* in_base = reinterpret_cast<char*>(const_cast<void*>(d.in)) + (size_t)d.in_choff * 2;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d.cout_pad};
+        cuuint64_t str[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {64, (cuuint32_t)(bn / 2)};
+        if (!encode_map(&p.tmW, const_cast<__half*>(d.w16), 2, dims, str, box, 128, err)) return -1;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)p.rows_alloc};
+        cuuint64_t str[1] = {(cuuint64_t)d.in_ld * 2};
+        cuuint32_t box[2] = {64, 128};
+        if (!encode_map(&p.tmA[0], in_base, 2, dims, str, box, 128, err)) return -1;
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)p.cout_store, (cuuint64_t)p.rows_alloc};
+        cuuint64_t str[1] = {(cuuint64_t)d.out_ld * 2};
+        cuuint32_t box[2] = {(cuuint32_t)gw, 32};
+        char* out_base = reinterpret_cast<char*>(d.out) + (size_t)d.out_choff * 2;
+        if (!encode_map(&p.tmOut, out_base, 2, dims, str, box, gw * 2, err)) return -1;
+    }
+    if (group < 1) group = 1;
+    if (group > p.num_kb) group = p.num_kb;
+    p.group = group;
+    const size_t epi_bytes = epi_slab_bytes(nepi, gw);
+    const size_t stage_bytes = ((size_t)128 * 64 * 2 + (size_t)(bn / 2) * 64 * 2) * group;
+    const size_t fixed = 1024 + epi_bytes + 16 * 8 + 192 + 4 * (size_t)d.cout_pad;
+    const size_t budget = (size_t)smem_budget_kb * 1024;
+    int S = budget > fixed ? (int)((budget - fixed) / stage_bytes) : 0;
+    if (S > 8) S = 8;
+    if (S < 2) return 0;
+    P.stages = S; p.stages = S;
+    p.n_tiles = d.cout_pad / bn;
+    p.bias_n = d.cout_pad;
+    P.smem = 1024 + S * stage_bytes + epi_bytes + 16 * S + 192 + 4 * (size_t)p.bias_n;
+    if (P.smem > 225 * 1024) return 0;
+    *pl = P;
+    return 1;
+}
+
+}  // namespace y4

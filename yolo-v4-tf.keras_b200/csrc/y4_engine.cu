@@ -27,6 +27,7 @@
 #include "kernels_simt.cuh"
 #include "decode_nms.cuh"
 #include "conv_tc.cuh"
+#include "conv_tc2.cuh"
 #include "conv0_tc.cuh"
 
 using namespace y4;
@@ -423,7 +424,7 @@ int run_conv(y4_engine* e, const ConvOp& c, int batch) {
     if (c.kind == 3) { launch_conv0_direct(e, c, batch); return Y4_OK; }
     if (c.kind == 4) { launch_conv0_tc(e, c, batch); return Y4_OK; }
     if (c.kind == 0) { launch_simt(e, c, batch); return Y4_OK; }
-    int rc = tc_launch(c.tc, batch, e->stream);
+    int rc = c.tc.cta2 ? tc2_launch(c.tc, batch, e->stream) : tc_launch(c.tc, batch, e->stream);
     if (rc != 0) return fail(e, Y4_ERR_CUDA, "tcgen05 conv launch failed for conv " + std::to_string(c.idx));
     e->launches++;
     return Y4_OK;
@@ -693,7 +694,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         // barrier x {A-patch reuse, resident weights} x epilogue {per-thread stores, slab + TMA store with 4 or 8 warps}.
         // Every candidate accumulates K in the same order and rounds once, so outputs are bit-identical across them
         // (and therefore across GPUs, whatever each one picks).
-        struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw; };
+        struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw, cta2; };
         std::vector<Cand> cands;
         const bool allow_patch = !(getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '0');
         const bool allow_bres = !(getenv("Y4_BRES") && getenv("Y4_BRES")[0] == '0');
@@ -701,8 +702,14 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         const int nepi_mode = getenv("Y4_NEPI") ? atoi(getenv("Y4_NEPI")) : 0;  // 4 / 8: only that many epilogue warps
         const int gw_mode = getenv("Y4_GW") ? atoi(getenv("Y4_GW")) : 0;        // 32 / 64: only that slab group width
         if (const char* f = getenv("Y4_FORCE")) {                                 // "bn,kb,patch,group,epi,nepi,bres,gw": that plan wherever it applies
-            Cand cd{}; if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d,%d", &cd.bn, &cd.kb, &cd.patch, &cd.group, &cd.epi, &cd.nepi, &cd.bres, &cd.gw) == 8) cands.push_back(cd);
+            Cand cd{}; if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d", &cd.bn, &cd.kb, &cd.patch, &cd.group, &cd.epi, &cd.nepi, &cd.bres, &cd.gw, &cd.cta2) >= 8) cands.push_back(cd);
         } else {
+            static const bool allow_cta2 = !(getenv("Y4_CTA2") && getenv("Y4_CTA2")[0] == '0');
+            if (allow_cta2)                                                      // CTA-pair kernel: {N tile, k-blocks per barrier, epilogue warps, group width}
+                for (int bn : {128, 256})
+                    for (int g : {1, 2, 3})
+                        for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}})
+                            cands.push_back({bn, 224, 0, g, 1, ep.first, 0, ep.second, 1});
             // {epilogue, epilogue warps, group width}
             const int epis[][3] = {{1, 4, 64}, {1, 4, 32}, {1, 8, 32}, {0, 4, 32}};
             for (int bn : {64, 128, 256})
@@ -716,7 +723,12 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                         for (int g : {1, 2, 3, 99}) cands.push_back({bn, 224, 0, g, epi, nepi, bres, gw});
                         if (!bres) cands.push_back({bn, 150, 0, 1, epi, nepi, 0, gw});
                     }
-                    if (allow_patch) { cands.push_back({bn, 224, 1, 1, epi, nepi, 0, gw}); cands.push_back({bn, 112, 1, 1, epi, nepi, 0, gw}); }
+                    if (allow_patch)                                            // 1: whole-halo patches, 3: one patch per kernel row
+                        for (int pm : {1, 3})
+                            for (int bres = 0; bres <= (allow_bres ? 1 : 0); bres++) {
+                                cands.push_back({bn, 224, pm, 1, epi, nepi, bres, gw});
+                                cands.push_back({bn, 112, pm, 1, epi, nepi, bres, gw});
+                            }
                 }
         }
         const char* at = getenv("Y4_AUTOTUNE");
@@ -738,7 +750,8 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                     const Cand& cd = cands[ci];
                     if (!cd.epi && epi_mode == 2 && best[li].p.epi) continue;
                     std::string er2;
-                    if (tc_plan(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw) != c.kind) continue;
+                    if (cd.cta2) { if (c.kind != 1 || tc_plan2(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.group, cd.nepi, cd.gw) != 1) continue; }
+                    else if (tc_plan(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw) != c.kind) continue;
                     has[li] = 1; any = true;
                 }
                 if (!any) continue;
@@ -1084,7 +1097,7 @@ int y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info) {
     info->flops = 2ll * c.N_OH * c.N_OH * c.cout * c.K;
     snprintf(info->out_name, sizeof(info->out_name), "%s", c.out_name.c_str());
     const bool tc = c.kind == 1 || c.kind == 2;
-    info->tc_mode = tc ? c.tc.p.mode : 0; info->tc_epilogue = tc && c.tc.p.epi ? c.tc.p.epi_gw : 0; info->tc_stages = tc ? c.tc.stages : 0;
+    info->tc_mode = tc ? (c.tc.cta2 ? 4 : c.tc.p.mode) : 0; info->tc_epilogue = tc && c.tc.p.epi ? c.tc.p.epi_gw : 0; info->tc_stages = tc ? c.tc.stages : 0;
     info->tc_group = tc ? c.tc.p.group : 0; info->tc_ctas_per_sm = tc ? c.tc.ctas_per_sm : 0; info->tc_bk = tc ? c.tc.bk : 0;
     info->tc_epi_warps = tc ? c.tc.nepi : 0; info->tc_resident_w = tc ? c.tc.p.bres : 0;
     return Y4_OK;
