@@ -1,0 +1,71 @@
+"""BASELINE config 4: decode + NMS isolation.  3-scale head tensors (76/38/19 grids at 608, 80 classes) crafted so that
+~1000 (box, class) candidates per image exceed the score threshold; the engine's decode + per-class NMS kernels are timed
+with the heads resident in HBM (CUDA events, L2 flushed between iterations) and compared with the oracle's CPU NMS
+(restatement of utils/custom_layers nms: custom_layers.py:261-298) on the same inputs; results must be bit-exact.
+usage: python tools/bench_decode_nms.py [size] [batch] -> one JSON line (also gpurun_out/decode_nms.json)"""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, 'oracle')]
+import numpy as np  # noqa: E402
+import y4b200  # noqa: E402
+import y4_oracle as O  # noqa: E402
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 608
+batch = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+heads = O.synth_heads(seed=4, batch=batch, img_size=size, n_clusters=150, per_cluster=7)
+eng = y4b200.Engine(img_size=size, max_batch=batch, precision=y4b200.PREC_FP16)
+eng.upload_heads(heads)
+for _ in range(3):
+    eng.run_decode_nms_resident(batch)
+eng.sync()
+times = []
+for _ in range(20):
+    eng.flush_l2()
+    eng.timer_begin()
+    eng.run_decode_nms_resident(batch)
+    times.append(eng.timer_end())
+ms = float(np.median(times))
+got = eng.fetch_results(batch)
+# hot-L2 figure as well (heads just written by the last conv layers is the in-pipeline situation)
+eng.timer_begin()
+for _ in range(20):
+    eng.run_decode_nms_resident(batch)
+ms_hot = eng.timer_end() / 20
+
+n_ref = min(batch, 4)                                  # the CPU oracle is timed on a bounded sample
+t0 = time.perf_counter()
+ref = O.decode_nms([h[:n_ref] for h in heads], size)
+cpu_s = time.perf_counter() - t0
+exact = all(np.array_equal(got[i][:n_ref], ref[i]) for i in (2, 3, 4))
+coord = float(max(np.abs(got[0][:n_ref] - ref[0]).max(), np.abs(got[1][:n_ref] - ref[1]).max()))
+N = sum(3 * (size // s) ** 2 for s in (8, 16, 32))
+cand = []
+for b in range(n_ref):
+    c = 0
+    for h in heads:
+        x = h[b].reshape(-1, 85)
+        obj = 1 / (1 + np.exp(-x[:, 4:5].astype(np.float64)))
+        cls = 1 / (1 + np.exp(-x[:, 5:].astype(np.float64)))
+        c += int(((obj * cls) > 0.3).sum())
+    cand.append(c)
+bytes_img = N * 85 * 4 + 2404
+pk = 6445.3
+try:
+    pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+except Exception:
+    pass
+line = {'workload': f'configs[3]: decode+NMS isolation, {size}x{size} heads, batch {batch}, 80 classes', 'candidates_per_image': cand,
+        'gpu_us_per_img': 1e3 * ms / batch, 'gpu_us_per_img_hot_l2': 1e3 * ms_hot / batch, 'gpu_ms_per_batch': ms,
+        'algorithmic_bytes_per_img': bytes_img, 'achieved_gbs': bytes_img * batch / (ms * 1e-3) / 1e9, 'hbm_peak_gbs': pk,
+        'frac_of_hbm_peak': bytes_img * batch / (ms * 1e-3) / 1e9 / pk,
+        'cpu_oracle_us_per_img': 1e6 * cpu_s / n_ref, 'cpu_cores': len(os.sched_getaffinity(0)), 'cpu_sample_images': n_ref,
+        'indices_classes_valid_bit_exact': bool(exact), 'max_abs_diff_boxes_scores': coord, 'launches_per_batch': 4}
+print(json.dumps(line))
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+with open(os.path.join(ROOT, 'gpurun_out', 'decode_nms.json'), 'w') as f:
+    f.write(json.dumps(line) + '\n')
+assert exact and coord <= 1e-4

@@ -46,74 +46,76 @@ __device__ __forceinline__ unsigned long long merge_key(int cls, float score, in
     return ((unsigned long long)(~__float_as_uint(score)) << 32) | ((unsigned long long)cls << 24) | (unsigned long long)box;
 }
 
-// One warp per grid cell (3 anchors x (5+nc) logits, contiguous in NHWC): coalesced read, sigmoid only
-// where obj > threshold can still pass (score = obj*cls <= obj), warp-aggregated append.
+// One thread per box (cell, anchor): objectness test first (score = obj * cls <= obj since cls <= 1 and the product is
+// rounded to nearest, so a box whose objectness fails can produce no candidate).  The few boxes that pass are then expanded
+// by the whole warp, one after the other: lanes take the classes, candidates are appended with one atomic per ballot, and
+// the box is decoded once if any class passed.  (The earlier warp-per-cell version spent its time launching 240 k warps per
+// batch that exit after three loads.)
 __global__ void __launch_bounds__(256) decode_filter_kernel(DecodeParams p) {
     const int lane = threadIdx.x & 31;
-    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int cells = p.cell_off[3];
-    if (gw >= (long long)p.batch * cells) return;
-    const int img = (int)(gw / cells);
-    const int cell = (int)(gw - (long long)img * cells);
-    const int s = cell < p.cell_off[1] ? 0 : (cell < p.cell_off[2] ? 1 : 2);
-    const int lc = cell - p.cell_off[s];
-    const int g = p.g[s];
-    const int row = lc / g, col = lc - row * g;
-    const float* ptr = p.padded[s]
-        ? p.head[s] + (((long long)img * (g + 2) + row + 1) * (g + 2) + col + 1) * p.ld[s]
-        : p.head[s] + (((long long)img * g + row) * g + col) * p.ld[s];
-
-    float obj[3];
-#pragma unroll
-    for (int a = 0; a < 3; a++) obj[a] = sigmoid_rn(ptr[a * p.C + 4]);
-    // score = obj * cls <= obj (cls <= 1, round-to-nearest product): nothing in this cell can pass -> warp-uniform exit
-    if (!(obj[0] > p.score_thr || obj[1] > p.score_thr || obj[2] > p.score_thr)) return;
-    unsigned anymask = 0;
-    const int total = 3 * p.C;
-    const int iters = (total + 31) >> 5;
-    for (int j = 0; j < iters; j++) {
-        const int e = lane + 32 * j;
-        bool cand = false;
-        float score = 0.f;
-        int a = 0, f = 0;
-        if (e < total) {
-            a = e / p.C;
-            f = e - a * p.C;
-            if (f >= 5 && obj[a] > p.score_thr) {
-                score = __fmul_rn(obj[a], sigmoid_rn(ptr[e]));       // confidence * class_probabilities (custom_layers.py:282)
-                cand = score > p.score_thr;                           // strict >
-            }
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, cand);
-        if (mask) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&p.cand_count[img], __popc(mask));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (cand) {
-                const int pos = base + __popc(mask & ((1u << lane) - 1u));
-                const int nbox = p.box_off[s] + lc * 3 + a;
-                if (pos < kCandCap) p.cand_keys[(long long)img * kCandCap + pos] = cand_key(f - 5, score, nbox);
-            }
-#pragma unroll
-            for (int k = 0; k < 3; k++)
-                if (__ballot_sync(0xffffffffu, cand && a == k)) anymask |= 1u << k;
-        }
+    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)p.batch * p.N;
+    int img = 0, n = 0, s = 0, lc = 0, a = 0, row = 0, col = 0;
+    const float* q = nullptr;
+    float obj = 0.f;
+    bool pass = false;
+    if (gt < total) {
+        img = (int)(gt / p.N);
+        n = (int)(gt - (long long)img * p.N);
+        s = n < p.box_off[1] ? 0 : (n < p.box_off[2] ? 1 : 2);
+        const int ln = n - p.box_off[s];
+        lc = ln / 3; a = ln - lc * 3;
+        const int g = p.g[s];
+        row = lc / g; col = lc - row * g;
+        const float* cellp = p.padded[s]
+            ? p.head[s] + (((long long)img * (g + 2) + row + 1) * (g + 2) + col + 1) * p.ld[s]
+            : p.head[s] + (((long long)img * g + row) * g + col) * p.ld[s];
+        q = cellp + a * p.C;
+        obj = sigmoid_rn(q[4]);
+        pass = obj > p.score_thr;
     }
-    if (anymask && lane < 3 && ((anymask >> lane) & 1u)) {
-        const int a = lane;
-        const float* q = ptr + a * p.C;
-        const float sx = sigmoid_rn(q[0]), sy = sigmoid_rn(q[1]);
-        const float bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, p.xyscale[s]), p.xyoff[s]), (float)col), p.stride[s]);
-        const float by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, p.xyscale[s]), p.xyoff[s]), (float)row), p.stride[s]);
-        const float bw = __fmul_rn(expf(q[2]), p.anchors[(s * 3 + a) * 2 + 0]);
-        const float bh = __fmul_rn(expf(q[3]), p.anchors[(s * 3 + a) * 2 + 1]);
-        const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);   // box_wh / 2 (exact)
-        float4 b;
-        b.x = __fdiv_rn(__fsub_rn(bx, hw), p.img_size);                   // boxes / input_shape[0]  (custom_layers.py:284)
-        b.y = __fdiv_rn(__fsub_rn(by, hh), p.img_size);
-        b.z = __fdiv_rn(__fadd_rn(bx, hw), p.img_size);
-        b.w = __fdiv_rn(__fadd_rn(by, hh), p.img_size);
-        p.boxes[(long long)img * p.N + p.box_off[s] + lc * 3 + a] = b;
+    unsigned todo = __ballot_sync(0xffffffffu, pass);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float* bq = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)q, src));
+        const float bobj = __shfl_sync(0xffffffffu, obj, src);
+        const int bimg = __shfl_sync(0xffffffffu, img, src), bn = __shfl_sync(0xffffffffu, n, src);
+        bool any = false;
+        for (int f0 = 0; f0 < p.nc; f0 += 32) {
+            const int f = f0 + lane;
+            bool cand = false;
+            float score = 0.f;
+            if (f < p.nc) {
+                score = __fmul_rn(bobj, sigmoid_rn(bq[5 + f]));          // confidence * class_probabilities (custom_layers.py:282)
+                cand = score > p.score_thr;                               // strict >
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, cand);
+            if (mask) {
+                any = true;
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&p.cand_count[bimg], __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (cand) {
+                    const int pos = base + __popc(mask & ((1u << lane) - 1u));
+                    if (pos < kCandCap) p.cand_keys[(long long)bimg * kCandCap + pos] = cand_key(f, score, bn);
+                }
+            }
+        }
+        if (any && lane == src) {
+            const float sx = sigmoid_rn(q[0]), sy = sigmoid_rn(q[1]);
+            const float bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, p.xyscale[s]), p.xyoff[s]), (float)col), p.stride[s]);
+            const float by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, p.xyscale[s]), p.xyoff[s]), (float)row), p.stride[s]);
+            const float bw = __fmul_rn(expf(q[2]), p.anchors[(s * 3 + a) * 2 + 0]);
+            const float bh = __fmul_rn(expf(q[3]), p.anchors[(s * 3 + a) * 2 + 1]);
+            const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);   // box_wh / 2 (exact)
+            float4 b;
+            b.x = __fdiv_rn(__fsub_rn(bx, hw), p.img_size);                   // boxes / input_shape[0]  (custom_layers.py:284)
+            b.y = __fdiv_rn(__fsub_rn(by, hh), p.img_size);
+            b.z = __fdiv_rn(__fadd_rn(bx, hw), p.img_size);
+            b.w = __fdiv_rn(__fadd_rn(by, hh), p.img_size);
+            p.boxes[(long long)img * p.N + n] = b;
+        }
     }
 }
 
@@ -158,8 +160,7 @@ struct NmsParams {
 constexpr int kBucketThreads = 1024;
 constexpr int kClassThreads = 128;
 constexpr int kClassSmemKeys = 1024;
-constexpr int kMergeThreads = 1024;
-constexpr size_t kMergeSmemBytes = (size_t)kSelCap * 8;
+constexpr int kMergeThreads = 256;                            // >= num_classes (255 max): one thread per class list
 
 __global__ void __launch_bounds__(kBucketThreads) nms_bucket_kernel(NmsParams p) {
     __shared__ int hist[256], cursor[256];
@@ -250,45 +251,39 @@ __global__ void __launch_bounds__(kClassThreads) nms_class_kernel(NmsParams p) {
 }
 
 __global__ void __launch_bounds__(kMergeThreads) nms_merge_kernel(NmsParams p) {
-    extern __shared__ __align__(16) unsigned char merge_smem[];
-    unsigned long long* wk = reinterpret_cast<unsigned long long*>(merge_smem);     // survivors, class-major, ascending inside a class
-    __shared__ int nw[256], off[257];
+    // k-way merge of the per-class survivor lists (each already score-descending = merge-key ascending): thread c holds the
+    // head of class c; max_boxes rounds of a block-wide min pick the output in order.  (Ranking every survivor against every
+    // class list cost 135 us per batch; the output only needs the first max_boxes of the merged order.)
+    __shared__ unsigned long long wmin[kMergeThreads / 32];
     __shared__ unsigned long long outkeys[kMaxBoxesCap];
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 256) nw[tid] = tid < p.nc ? p.nwin[img * 256 + tid] : 0;
-    __syncthreads();
-    if (tid < 32) {
-        int v[8], s = 0;
+    const unsigned long long kNone = ~0ull;
+    const unsigned long long* list = p.win_keys + ((long long)img * p.nc + tid) * p.max_boxes;
+    const int cnt = tid < p.nc ? p.nwin[img * 256 + tid] : 0;
+    int cur = 0;
+    unsigned long long head = cnt > 0 ? list[0] : kNone;
+    unsigned long long nxt = cnt > 1 ? list[1] : kNone;       // one element of lookahead hides the global-load latency
+    int nvalid = 0;
+    for (int k = 0; k < p.max_boxes; k++) {
+        unsigned long long m = head;
 #pragma unroll
-        for (int j = 0; j < 8; j++) { v[j] = nw[lane * 8 + j]; s += v[j]; }
-        int incl = s;
+        for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d); m = o < m ? o : m; }
+        if (lane == 0) wmin[warp] = m;
+        __syncthreads();
+        unsigned long long best = wmin[0];
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-        int run = incl - s;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { off[lane * 8 + j] = run; run += v[j]; }
-        if (lane == 31) off[256] = run;
-    }
-    __syncthreads();
-    const int ntot = off[256];
-    for (int c = warp; c < p.nc; c += (kMergeThreads >> 5)) {
-        const unsigned long long* src = p.win_keys + ((long long)img * p.nc + c) * p.max_boxes;
-        for (int i = lane; i < nw[c]; i += 32) wk[off[c] + i] = src[i];
-    }
-    __syncthreads();
-    for (int i = tid; i < ntot; i += kMergeThreads) {
-        const unsigned long long k = wk[i];
-        int r = 0;
-        for (int c = 0; c < p.nc && r < p.max_boxes; c++) {
-            int lo = 0, hi = nw[c];                        // lower bound of k in class c's ascending list
-            const unsigned long long* a = wk + off[c];
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (a[mid] < k) lo = mid + 1; else hi = mid; }
-            r += lo;
+        for (int w = 1; w < kMergeThreads / 32; w++) best = wmin[w] < best ? wmin[w] : best;
+        __syncthreads();
+        if (best == kNone) break;                             // block-uniform: every list is exhausted
+        if (tid == 0) outkeys[k] = best;
+        nvalid = k + 1;
+        if (head == best) {                                   // keys are unique: exactly one owner
+            cur++;
+            head = nxt;
+            nxt = cur + 1 < cnt ? list[cur + 1] : kNone;
         }
-        if (r < p.max_boxes) outkeys[r] = k;
     }
     __syncthreads();
-    const int nvalid = ntot < p.max_boxes ? ntot : p.max_boxes;
     const float4* boxes = p.boxes + (long long)img * p.N;
     if (tid == 0) p.out_valid[img] = nvalid;
     for (int k = tid; k < p.max_boxes; k += kMergeThreads) {

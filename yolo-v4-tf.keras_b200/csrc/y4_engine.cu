@@ -457,8 +457,7 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
     d.nc = nc; d.C = 5 + nc; d.N = e->N; d.batch = batch; d.img_size = (float)e->cfg.img_size; d.score_thr = score_thr;
     d.cand_keys = e->d_cand_keys; d.cand_count = e->d_cand_count; d.boxes = e->d_boxes;
     CUDA_TRY(e, cudaMemsetAsync(e->d_cand_count, 0, sizeof(int) * batch, e->stream));
-    long long warps = (long long)batch * cells;
-    unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+    unsigned blocks = (unsigned)(((long long)batch * e->N + 255) / 256);       // one thread per box
     decode_filter_kernel<<<blocks, 256, 0, e->stream>>>(d);
     NmsParams n{};
     n.cand_keys = e->d_cand_keys; n.cand_count = e->d_cand_count; n.boxes = e->d_boxes;
@@ -469,7 +468,7 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
     n.win_keys = e->d_win_keys; n.nwin = e->d_nwin;
     nms_bucket_kernel<<<batch, kBucketThreads, 0, e->stream>>>(n);
     nms_class_kernel<<<batch * nc, kClassThreads, 0, e->stream>>>(n);
-    nms_merge_kernel<<<batch, kMergeThreads, kMergeSmemBytes, e->stream>>>(n);
+    nms_merge_kernel<<<batch, kMergeThreads, 0, e->stream>>>(n);
     e->launches += 4;
     CUDA_TRY(e, cudaGetLastError());
     return Y4_OK;
@@ -657,7 +656,6 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     CREATE_TRY(cudaMemset(e->d_overflow, 0, sizeof(int)));
     e->flush_elems = (size_t)(192u << 20) / sizeof(float4);      // 192 MB > 126 MB L2
     CREATE_TRY(cudaMalloc(&e->d_flush, e->flush_elems * sizeof(float4)));
-    CREATE_TRY(cudaFuncSetAttribute(nms_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMergeSmemBytes));
     // tcgen05 plans (tensor maps need the buffer addresses, which are now fixed)
     if (cfg->precision == Y4_PREC_FP16 || cfg->precision == Y4_PREC_FP16X3) {
         const bool split = cfg->precision == Y4_PREC_FP16X3;
@@ -706,7 +704,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         } else {
             static const bool allow_cta2 = !(getenv("Y4_CTA2") && getenv("Y4_CTA2")[0] == '0');
             if (allow_cta2)                                                      // CTA-pair kernel: {N tile, k-blocks per barrier, epilogue warps, group width}
-                for (int bn : {128, 256})
+                for (int bn : {64, 128, 256})
                     for (int g : {1, 2, 3})
                         for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}})
                             cands.push_back({bn, 224, 0, g, 1, ep.first, 0, ep.second, 1});
