@@ -272,11 +272,39 @@ def main():
         t = torch.tensor([e2e_dt], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
+    # raw 8-bit images, the form the reference's callers hold (cv2.imread -> preprocess_img -> predict, models.py:95-127,141-179):
+    # H2D of the uint8 pixels, resize + /255 on the GPU, forward, decode, NMS, D2H of the detections
+    raws = [binding.pinned_array((S, S, 3), np.uint8) for _ in range(2 * B)]
+    rng = np.random.default_rng(1234 + rank)
+    for r in raws:
+        r[...] = rng.integers(0, 256, (S, S, 3), dtype=np.uint8)
+    rb = [raws[:B], raws[B:]]
+    for i in range(3):
+        eng.submit_u8(rb[i & 1])
+        eng.collect()
+    barrier()
+    t0 = time.perf_counter()
+    eng.submit_u8(rb[0])
+    for i in range(1, e2e_steps):
+        eng.submit_u8(rb[i & 1])
+        out8 = eng.collect()
+    out8 = eng.collect()
+    barrier()
+    e2e8_dt = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e8_dt], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e8_dt = float(t.item())
     mb = eng.max_boxes
-    e2e = {'value': world * B * e2e_steps / e2e_dt, 'unit': 'images/s', 'h2d_bytes_per_step': int(imgs.nbytes),
-           'd2h_bytes_per_step': int(B * (mb * 4 * 4 + mb * 4 * 3 + 4)), 'steps': e2e_steps,
-           'api': 'y4_submit/y4_collect, depth 2 (host float32 NHWC in pinned memory -> detections in host memory)',
-           'blocking_call_value': world * B * e2e_steps / e2e_sync_dt, 'blocking_call_api': 'y4_predict'}
+    d2h = int(B * (mb * 4 * 4 + mb * 4 * 3 + 4))
+    e2e = {'value': world * B * e2e_steps / e2e8_dt, 'unit': 'images/s', 'h2d_bytes_per_step': int(B * S * S * 3),
+           'd2h_bytes_per_step': d2h, 'steps': e2e_steps,
+           'api': 'y4_submit_u8/y4_collect, depth 2: raw uint8 HWC images in pinned host memory -> GPU resize (cv2 INTER_LINEAR semantics) + /255 '
+                  '-> forward -> decode -> NMS -> detections in host memory (what Yolov4.export_prediction calls)',
+           'float32_input': {'value': world * B * e2e_steps / e2e_dt, 'h2d_bytes_per_step': int(imgs.nbytes),
+                             'api': 'y4_submit/y4_collect with already preprocessed float32 NHWC images'},
+           'blocking_call_value': world * B * e2e_steps / e2e_sync_dt, 'blocking_call_api': 'y4_predict (float32 input, no overlap)'}
 
     if rank != 0:
         return

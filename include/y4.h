@@ -140,6 +140,21 @@ int64_t y4_launch_count(const y4_engine* e);
 int  y4_profile_layers(y4_engine* e, int32_t batch, float* ms, int32_t n);
 
 /* Pinned host memory for callers that want async H2D/D2H. */
+/* ---- raw 8-bit images: preprocess_img + predict (models.py:95-98, 109-127, 141-179) --------------------
+ * imgs[i]: host uint8 HWC (heights[i], widths[i], 3), densely packed (what cv2.imread returns).  Each image is resized on
+ * the GPU to (S, S) with OpenCV's 8-bit INTER_LINEAR fixed-point arithmetic (bit-exact with cv2.resize), divided by 255 in
+ * float64 and rounded to float32 (Keras' input cast); aspect ratio is not preserved (models.py:96).
+ * reverse_channels = 1 reproduces predict()'s BGR->RGB flip (models.py:126); export_prediction / predict_raw pass 0.
+ * H2D traffic is 1 byte per source pixel-channel instead of 4 bytes per resized one. */
+int  y4_predict_u8(y4_engine* e, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths, int32_t batch,
+                   int32_t reverse_channels, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx);
+/* Only the preprocessing: out (nullable) receives the (batch, S, S, 3) float32 network input (parity tests). */
+int  y4_preprocess_u8(y4_engine* e, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths, int32_t batch,
+                      int32_t reverse_channels, float* out);
+/* Pipelined form of y4_predict_u8: pair with y4_collect, same rules as y4_submit. */
+int  y4_submit_u8(y4_engine* e, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths, int32_t batch,
+                  int32_t reverse_channels);
+
 void* y4_host_alloc(size_t nbytes);
 void  y4_host_free(void* p);
 

@@ -381,9 +381,44 @@ def predict(imgs, W: Weights, margins=None, dtype=np.float32):
 # ----------------------------------------------------------------------------------------------
 # host-side pieces of the API  (models.py:95-98, utils.py:56-78)
 # ----------------------------------------------------------------------------------------------
+def resize_linear_u8(img_u8, W, H):
+    """cv2.resize(img, (W, H)) for 8-bit images, interpolation INTER_LINEAR (the default the reference uses,
+    models.py:96), restated from OpenCV's fixed-point path (opencv/modules/imgproc/src/resize.cpp: resizeGeneric_ /
+    HResizeLinear / VResizeLinear<uchar,int,short>, INTER_RESIZE_COEF_BITS = 11).  OpenCV is a third-party dependency of the
+    reference (unpinned; 4.13.0 in this image); tests/test_oracle.py pins this restatement bit-exactly against cv2.resize on
+    the reference's own images."""
+    img = np.ascontiguousarray(img_u8, dtype=np.uint8)
+    h, w = img.shape[:2]
+    dx = np.arange(W, dtype=np.float64)
+    fx = ((dx + 0.5) * (w / W) - 0.5).astype(np.float32)
+    sx = np.floor(fx).astype(np.int64)
+    fx = (fx - sx.astype(np.float32)).astype(np.float32)
+    lo, hi = sx < 0, sx >= w - 1
+    fx[lo] = 0; sx[lo] = 0
+    fx[hi] = 0; sx[hi] = w - 1
+    a1 = np.rint(fx * np.float32(2048)).astype(np.int64)                 # saturate_cast<short>: round half to even
+    a0 = np.rint((np.float32(1) - fx) * np.float32(2048)).astype(np.int64)
+    sx1 = np.minimum(sx + 1, w - 1)
+    dy = np.arange(H, dtype=np.float64)
+    fy = ((dy + 0.5) * (h / H) - 0.5).astype(np.float32)
+    sy = np.floor(fy).astype(np.int64)
+    fy = (fy - sy.astype(np.float32)).astype(np.float32)
+    b1 = np.rint(fy * np.float32(2048)).astype(np.int64)
+    b0 = np.rint((np.float32(1) - fy) * np.float32(2048)).astype(np.int64)
+    sy0, sy1 = np.clip(sy, 0, h - 1), np.clip(sy + 1, 0, h - 1)
+    src = img.astype(np.int64).reshape(h, w, -1)
+
+    def hpass(rows):
+        r = src[rows]
+        return r[:, sx, :] * a0[None, :, None] + r[:, sx1, :] * a1[None, :, None]
+    t0, t1 = hpass(sy0), hpass(sy1)
+    out = (((b0[:, None, None] * (t0 >> 4)) >> 16) + ((b1[:, None, None] * (t1 >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8).reshape((H, W) + img.shape[2:])
+
+
 def preprocess_img(img_u8, size):
-    import cv2
-    return cv2.resize(img_u8, (size, size)) / 255.0          # float64, no letterbox
+    """models.py:95-98: cv2.resize(img, (W, H)) / 255.  -> float64 (Keras casts to float32 at predict)."""
+    return resize_linear_u8(img_u8, size, size) / 255.0      # no letterbox: aspect ratio is not preserved
 
 
 def detection_table(raw_hw, outputs, class_names):

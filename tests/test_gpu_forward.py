@@ -187,3 +187,46 @@ def test_submit_collect_matches_predict(weights):
         for a, b in zip(r, g):
             assert np.array_equal(a, b)
     eng.close()
+
+
+def test_preprocess_u8_matches_cv2_golden_and_oracle():
+    """GPU preprocess (resize + /255) == cv2.resize golden vectors of the reference's image, bit for bit, and == the
+    oracle on random images of mixed sizes in one batch; reverse_channels is predict()'s BGR->RGB flip."""
+    import os
+    import y4b200
+    import y4_oracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'preprocess_street.npz'))
+    raw = g['raw']
+    eng = y4b200.Engine(img_size=160, max_batch=4, precision=y4b200.PREC_FP16)
+    got = eng.preprocess_u8([raw])
+    want = (g['resize_160'] / 255.).astype(np.float32)
+    assert np.array_equal(got[0], want)
+    rng = np.random.default_rng(3)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for (h, w) in [(37, 53), (333, 517), (700, 300), (160, 160)]]
+    got = eng.preprocess_u8(imgs)
+    for i, im in enumerate(imgs):
+        assert np.array_equal(got[i], O.preprocess_img(im, 160).astype(np.float32)), i
+    flipped = eng.preprocess_u8(imgs, reverse_channels=True)
+    assert np.array_equal(flipped, got[..., ::-1])
+    eng.close()
+
+
+def test_predict_u8_equals_predict_on_preprocessed(weights):
+    """y4_predict_u8 / y4_submit_u8 == y4_predict on the oracle-preprocessed float images."""
+    import y4b200
+    import y4_oracle as O
+    W, blob = weights
+    S, B = 160, 2
+    eng = y4b200.Engine(img_size=S, max_batch=B, precision=y4b200.PREC_FP16)
+    eng.load_darknet_bytes(blob)
+    rng = np.random.default_rng(5)
+    raws = [rng.integers(0, 256, (120, 200, 3), dtype=np.uint8), rng.integers(0, 256, (300, 180, 3), dtype=np.uint8)]
+    ref = eng.predict(np.stack([O.preprocess_img(r, S) for r in raws]), with_indices=True)
+    got = eng.predict_u8(raws, with_indices=True)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
+    eng.submit_u8(raws)
+    got2 = eng.collect(with_indices=True)
+    for a, b in zip(got2, ref):
+        assert np.array_equal(a, b)
+    eng.close()

@@ -196,3 +196,37 @@ def test_oracle_predict_small(weights):
     heads_f = O.forward(imgs, W, fold_bn=True)
     for a, b in zip(heads, heads_f):                    # BN folding is exact up to fp32 round-off
         assert np.abs(a - b).max() / np.abs(a).max() < 1e-4
+
+
+# ---- preprocess_img: oracle restatement pinned to the reference's dependency (cv2.resize) -------------------------
+def _golden_pre():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'preprocess_street.npz'))
+
+
+def test_resize_restatement_matches_cv2_golden():
+    """Golden vectors produced by cv2.resize on the reference's img/street.jpeg (tests/golden/make_golden_preprocess.py):
+    the fixed-point restatement is bit-exact, for down-, up-scaling and odd sizes."""
+    import hashlib
+    import y4_oracle as O
+    g = _golden_pre()
+    raw = g['raw']
+    assert np.array_equal(O.resize_linear_u8(raw, 160, 160), g['resize_160'])
+    for S in (320, 416, 608):
+        r = O.resize_linear_u8(raw, S, S)
+        assert hashlib.sha256(r.tobytes()).hexdigest() == str(g[f'sha256_{S}'])
+        pre = O.preprocess_img(raw, S)
+        assert pre.dtype == np.float64 and pre.shape == (S, S, 3)
+        assert abs(float(pre.astype(np.float32).astype(np.float64).sum()) - float(g[f'pre_f32_sum_{S}'])) < 1e-6
+    assert np.array_equal(O.resize_linear_u8(g['crop'], 64, 96), g['crop_resize_64x96'])
+    assert np.array_equal(O.resize_linear_u8(g['crop'], 301, 257), g['crop_resize_301x257'])
+
+
+def test_resize_restatement_matches_cv2_live():
+    """Where cv2 is importable (this image), compare against it directly on random images and sizes."""
+    cv2 = pytest.importorskip('cv2')
+    import y4_oracle as O
+    rng = np.random.default_rng(7)
+    for (h, w, S) in [(37, 53, 64), (333, 517, 416), (700, 300, 320), (64, 64, 608), (5, 9, 96)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        assert np.array_equal(O.resize_linear_u8(img, S, S), cv2.resize(img, (S, S))), (h, w, S)

@@ -36,7 +36,7 @@ class Y4LayerInfo(C.Structure):
 
 EXPORTS = [
     'y4_default_config', 'y4_create', 'y4_destroy', 'y4_last_error', 'y4_load_darknet',
-    'y4_load_darknet_from_memory', 'y4_predict', 'y4_submit', 'y4_collect', 'y4_forward_heads', 'y4_decode_nms', 'y4_synth_fill',
+    'y4_load_darknet_from_memory', 'y4_predict', 'y4_predict_u8', 'y4_preprocess_u8', 'y4_submit', 'y4_submit_u8', 'y4_collect', 'y4_forward_heads', 'y4_decode_nms', 'y4_synth_fill',
     'y4_run_resident', 'y4_run_forward_resident', 'y4_run_decode_nms_resident', 'y4_upload_heads',
     'y4_fetch_results', 'y4_sync', 'y4_timer_begin', 'y4_timer_end', 'y4_flush_l2', 'y4_launch_count',
     'y4_profile_layers', 'y4_host_alloc', 'y4_host_free', 'y4_num_layers', 'y4_describe_layer', 'y4_num_boxes',
@@ -65,6 +65,9 @@ def load_library():
     lib.y4_load_darknet_from_memory.argtypes = [vp, vp, C.c_size_t]
     lib.y4_predict.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.y4_submit.argtypes = [vp, vp, C.c_int32]
+    lib.y4_predict_u8.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
+    lib.y4_preprocess_u8.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_int32, vp]
+    lib.y4_submit_u8.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_int32]
     lib.y4_collect.argtypes = [vp, C.c_int32, vp, vp, vp, vp, vp]
     lib.y4_forward_heads.argtypes = [vp, vp, C.c_int32, vp, vp, vp]
     lib.y4_decode_nms.argtypes = [vp, vp, vp, vp, C.c_int32, C.c_float, C.c_float, vp, vp, vp, vp, vp]
@@ -188,6 +191,40 @@ class Engine:
         boxes, scores, classes, valid, idx = self._alloc_out(b)
         self._chk(self._lib.y4_predict(self._h, _ptr(imgs), b, _ptr(boxes), _ptr(scores), _ptr(classes), _ptr(valid), _ptr(idx)))
         return (boxes, scores, classes, valid, idx) if with_indices else [boxes, scores, classes, valid]
+
+    # ---- raw 8-bit images (GPU preprocess: cv2.resize INTER_LINEAR semantics + /255)
+    def _u8_table(self, imgs):
+        imgs = [np.ascontiguousarray(im, dtype=np.uint8) for im in imgs]
+        for im in imgs:
+            if im.ndim != 3 or im.shape[2] != 3:
+                raise ValueError(f'raw images must be (h, w, 3) uint8, got {im.shape}')
+        n = len(imgs)
+        ptrs = (C.c_void_p * n)(*[im.ctypes.data for im in imgs])
+        hs = np.array([im.shape[0] for im in imgs], np.int32)
+        ws = np.array([im.shape[1] for im in imgs], np.int32)
+        return imgs, ptrs, hs, ws
+
+    def preprocess_u8(self, imgs, reverse_channels=False):
+        """(batch, S, S, 3) float32 network input the engine builds from raw uint8 images (== preprocess_img, models.py:95-98)."""
+        imgs, ptrs, hs, ws = self._u8_table(imgs)
+        out = np.zeros((len(imgs), self.img_size, self.img_size, 3), np.float32)
+        self._chk(self._lib.y4_preprocess_u8(self._h, ptrs, _ptr(hs), _ptr(ws), len(imgs), int(reverse_channels), _ptr(out)))
+        return out
+
+    def predict_u8(self, imgs, reverse_channels=False, with_indices=False):
+        imgs, ptrs, hs, ws = self._u8_table(imgs)
+        b = len(imgs)
+        boxes, scores, classes, valid, idx = self._alloc_out(b)
+        self._chk(self._lib.y4_predict_u8(self._h, ptrs, _ptr(hs), _ptr(ws), b, int(reverse_channels),
+                                          _ptr(boxes), _ptr(scores), _ptr(classes), _ptr(valid), _ptr(idx)))
+        return (boxes, scores, classes, valid, idx) if with_indices else [boxes, scores, classes, valid]
+
+    def submit_u8(self, imgs, reverse_channels=False):
+        """Pipelined form of predict_u8 (keep the arrays alive until the matching collect())."""
+        imgs, ptrs, hs, ws = self._u8_table(imgs)
+        self._chk(self._lib.y4_submit_u8(self._h, ptrs, _ptr(hs), _ptr(ws), len(imgs), int(reverse_channels)))
+        self._inflight = getattr(self, '_inflight', []) + [np.empty((len(imgs), 0))]
+        self._keep = getattr(self, '_keep', [])[-4:] + [(imgs, ptrs, hs, ws)]
 
     def submit(self, imgs):
         """Pipelined path: enqueue one batch (keep `imgs` alive and unmodified until the matching collect())."""

@@ -29,6 +29,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "conv0_tc.cuh"
+#include "preprocess.cuh"
 
 using namespace y4;
 
@@ -115,6 +116,10 @@ struct y4_engine {
     char* stage[2] = {nullptr, nullptr};          // pinned: boxes | scores | classes | idx | valid | overflow
     int64_t n_submitted = 0, n_collected = 0;
     int sub_batch[2] = {0, 0};
+    // raw 8-bit input path (y4_predict_u8 / y4_submit_u8): device staging for the source images, one per input slot
+    uint8_t* d_u8[2] = {nullptr, nullptr}; size_t u8_cap[2] = {0, 0};
+    PreImage* d_pre[2] = {nullptr, nullptr}; PreImage* h_pre[2] = {nullptr, nullptr};
+    bool div255_ready = false;
 };
 
 namespace {
@@ -801,6 +806,7 @@ void y4_destroy(y4_engine* e) {
     for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_w16k32); cudaFree(c.d_w16_lo); cudaFree(c.d_wscale); cudaFree(c.d_bias); }
     cudaFree(e->d_img_slot[0]); cudaFree(e->d_img_slot[1]);
     for (int i = 0; i < 2; i++) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); if (e->stage[i]) cudaFreeHost(e->stage[i]); }
+    for (int i = 0; i < 2; i++) { cudaFree(e->d_u8[i]); cudaFree(e->d_pre[i]); if (e->h_pre[i]) cudaFreeHost(e->h_pre[i]); }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 3; i++) cudaFree(e->d_user_heads[i]);
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
@@ -970,9 +976,78 @@ static size_t stage_bytes(const y4_engine* e) {
     const size_t mb = e->cfg.max_boxes, B = e->cfg.max_batch;
     return B * (mb * 4 * 4 + mb * 4 * 3 + 4) + 16;
 }
-int y4_submit(y4_engine* e, const float* imgs, int32_t batch) {
+// Source images -> device staging (on `cs`), then the resize + /255 kernel writes the network input of `slot` (on `cs` too,
+// so the caller orders the compute stream behind one event).
+static int stage_u8(y4_engine* e, int slot, const uint8_t* const* imgs, const int32_t* hs, const int32_t* ws, int batch, int reverse, cudaStream_t cs) {
+    if (!imgs || !hs || !ws) return fail(e, Y4_ERR_ARG, "null image table");
+    const int S = e->cfg.img_size, B = e->cfg.max_batch;
+    size_t total = 0;
+    for (int i = 0; i < batch; i++) {
+        if (!imgs[i] || hs[i] < 1 || ws[i] < 1 || hs[i] > 32768 || ws[i] > 32768) return fail(e, Y4_ERR_ARG, "bad image in the batch");
+        total += ((size_t)hs[i] * ws[i] * 3 + 255) & ~(size_t)255;
+    }
+    if (!e->div255_ready) {
+        float lut[256];
+        for (int i = 0; i < 256; i++) lut[i] = (float)((double)i / 255.0);           // img / 255. in float64, then Keras' float32 cast
+        CUDA_TRY(e, cudaMemcpyToSymbol(c_div255, lut, sizeof(lut)));
+        e->div255_ready = true;
+    }
+    if (!e->d_pre[slot]) {
+        CUDA_TRY(e, cudaMalloc(&e->d_pre[slot], sizeof(PreImage) * B));
+        CUDA_TRY(e, cudaHostAlloc((void**)&e->h_pre[slot], sizeof(PreImage) * B, cudaHostAllocDefault));
+    }
+    if (total > e->u8_cap[slot]) {
+        CUDA_TRY(e, cudaStreamSynchronize(cs));
+        cudaFree(e->d_u8[slot]); e->d_u8[slot] = nullptr; e->u8_cap[slot] = 0;
+        const size_t cap = total + total / 4;
+        CUDA_TRY(e, cudaMalloc(&e->d_u8[slot], cap));
+        e->u8_cap[slot] = cap;
+    }
+    size_t off = 0;
+    for (int i = 0; i < batch; i++) {
+        const size_t n = (size_t)hs[i] * ws[i] * 3;
+        e->h_pre[slot][i] = PreImage{(long long)off, hs[i], ws[i]};
+        CUDA_TRY(e, cudaMemcpyAsync(e->d_u8[slot] + off, imgs[i], n, cudaMemcpyHostToDevice, cs));
+        off += (n + 255) & ~(size_t)255;
+    }
+    CUDA_TRY(e, cudaMemcpyAsync(e->d_pre[slot], e->h_pre[slot], sizeof(PreImage) * batch, cudaMemcpyHostToDevice, cs));
+    dim3 grid((unsigned)((S + 255) / 256), (unsigned)S, (unsigned)batch);
+    preprocess_u8_kernel<<<grid, 256, 0, cs>>>(e->d_u8[slot], e->d_pre[slot], e->d_img_slot[slot], S, batch, reverse);
+    e->launches++;
+    CUDA_TRY(e, cudaGetLastError());
+    return Y4_OK;
+}
+
+int y4_preprocess_u8(y4_engine* e, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths, int32_t batch,
+                     int32_t reverse_channels, float* out) {
+    int rc = ready(e, batch, false); if (rc) return rc;
+    rc = stage_u8(e, 0, imgs, heights, widths, batch, reverse_channels, e->stream); if (rc) return rc;
+    if (out) CUDA_TRY(e, cudaMemcpyAsync(out, e->d_img_slot[0], sizeof(float) * 3 * e->cfg.img_size * e->cfg.img_size * batch, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    return Y4_OK;
+}
+
+int y4_predict_u8(y4_engine* e, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths, int32_t batch,
+                  int32_t reverse_channels, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx) {
     int rc = ready(e, batch, true); if (rc) return rc;
-    if (!imgs) return fail(e, Y4_ERR_ARG, "null imgs");
+    rc = stage_u8(e, 0, imgs, heights, widths, batch, reverse_channels, e->stream); if (rc) return rc;
+    rc = run_resident_part(e, batch, 3); if (rc) return rc;
+    return fetch(e, batch, boxes, scores, classes, valid, cand_idx);
+}
+
+static int submit_common(y4_engine* e, int32_t batch, const float* imgs, const uint8_t* const* u8, const int32_t* hs, const int32_t* ws, int reverse);
+
+int y4_submit_u8(y4_engine* e, const uint8_t* const* imgs, const int32_t* heights, const int32_t* widths, int32_t batch, int32_t reverse_channels) {
+    return submit_common(e, batch, nullptr, imgs, heights, widths, reverse_channels);
+}
+
+int y4_submit(y4_engine* e, const float* imgs, int32_t batch) {
+    if (!imgs) return e ? fail(e, Y4_ERR_ARG, "null imgs") : Y4_ERR_ARG;
+    return submit_common(e, batch, imgs, nullptr, nullptr, nullptr, 0);
+}
+
+static int submit_common(y4_engine* e, int32_t batch, const float* imgs, const uint8_t* const* u8, const int32_t* hs, const int32_t* ws, int reverse) {
+    int rc = ready(e, batch, true); if (rc) return rc;
     if (e->n_submitted - e->n_collected >= 2) return fail(e, Y4_ERR_STATE, "two batches already in flight: call y4_collect first");
     const int S = e->cfg.img_size, B = e->cfg.max_batch, mb = e->cfg.max_boxes;
     if (!e->copy_stream) {
@@ -987,7 +1062,8 @@ int y4_submit(y4_engine* e, const float* imgs, int32_t batch) {
     const int slot = (int)(e->n_submitted & 1);
     // the slot's previous occupant (submit n-2) was collected, hence its compute (which read d_img_slot[slot]) is done
     const size_t n = (size_t)batch * S * S * 3;
-    CUDA_TRY(e, cudaMemcpyAsync(e->d_img_slot[slot], imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    if (imgs) CUDA_TRY(e, cudaMemcpyAsync(e->d_img_slot[slot], imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->copy_stream));
+    else { rc = stage_u8(e, slot, u8, hs, ws, batch, reverse, e->copy_stream); if (rc) return rc; }
     CUDA_TRY(e, cudaEventRecord(e->ev_h2d[slot], e->copy_stream));
     CUDA_TRY(e, cudaStreamWaitEvent(e->stream, e->ev_h2d[slot], 0));
     e->d_img = e->d_img_slot[slot]; e->img_slot = slot;

@@ -58,11 +58,20 @@ class Yolov4(object):
         parts = [self.engine.predict(imgs[i:i + mb]) for i in range(0, len(imgs), mb)]
         return [np.concatenate([p[k] for p in parts], axis=0) for k in range(4)]
 
+    def _predict_raw_u8(self, raws, reverse_channels=False):
+        """preprocess_img + inference_model.predict for raw uint8 images, both on the GPU (y4_predict_u8)."""
+        mb = self.engine.max_batch
+        parts = [self.engine.predict_u8(raws[i:i + mb], reverse_channels=reverse_channels) for i in range(0, len(raws), mb)]
+        return [np.concatenate([p[k] for p in parts], axis=0) for k in range(4)]
+
     # raw_img: RGB
     def predict_img(self, raw_img, random_color=True, plot_img=True, figsize=(10, 10), show_text=True, return_output=False):
         print('img shape: ', raw_img.shape)
-        img = self.preprocess_img(raw_img)
-        pred_output = self._predict_batches(np.expand_dims(img, axis=0))
+        if raw_img.dtype == np.uint8:                    # the normal case (cv2.imread): resize + /255 run on the GPU
+            pred_output = self._predict_raw_u8([raw_img])
+        else:
+            img = self.preprocess_img(raw_img)
+            pred_output = self._predict_batches(np.expand_dims(img, axis=0))
         detections = get_detection_data(img=raw_img, model_outputs=pred_output, class_names=self.class_names)
         output_img = draw_bbox(raw_img, detections, cmap=self.class_color, random_color=random_color,
                                figsize=figsize, show_text=show_text, show_img=plot_img)
@@ -93,26 +102,36 @@ class Yolov4(object):
         return detections
 
     def export_prediction(self, annotation_path, pred_folder_path, img_folder_path, bs=2):
-        """Batched caller (models.py:141-179): `<class> <score> <x1> <y1> <x2> <y2>` per detection, raw-image px."""
+        """Batched caller (models.py:141-179): `<class> <score> <x1> <y1> <x2> <y2>` per detection, raw-image px.
+        Pipelined: while the GPU works on batch i (H2D of the raw bytes, resize, forward, decode, NMS), the host decodes the
+        files of batch i+1 and writes the text files of batch i-1 (y4_submit_u8 / y4_collect, two batches in flight)."""
         import cv2
         with open(annotation_path) as file:
             img_paths = [os.path.join(img_folder_path, line.split(' ')[0].split(os.sep)[-1]) for line in file]
-        for start in range(0, len(img_paths), bs):
-            paths = img_paths[start:start + bs]
-            imgs = np.zeros((len(paths), *self.img_size))
-            shapes = []
-            for j, path in enumerate(paths):
-                img = cv2.imread(path)                    # BGR kept (no flip), models.py:153
-                shapes.append(img.shape)
-                imgs[j] = self.preprocess_img(img)
-            b_boxes, b_scores, b_classes, b_valid = self._predict_batches(imgs)
+        bs = max(1, min(int(bs), self.engine.max_batch))
+
+        def write(paths, raws, outs):
+            b_boxes, b_scores, b_classes, b_valid = outs[:4]
             for k, path in enumerate(paths):
                 n = int(b_valid[k])
                 boxes = b_boxes[k, :n].copy()
-                boxes[:, [0, 2]] *= shapes[k][1]
-                boxes[:, [1, 3]] *= shapes[k][0]
+                boxes[:, [0, 2]] *= raws[k].shape[1]
+                boxes[:, [1, 3]] *= raws[k].shape[0]
                 stem = path.split(os.sep)[-1].split('.')[0]
                 with open(os.path.join(pred_folder_path, stem + '.txt'), 'w') as out:
                     for i in range(n):
                         bx = boxes[i]
                         out.write(f'{self.class_names[int(b_classes[k, i])]} {b_scores[k, i]} {bx[0]} {bx[1]} {bx[2]} {bx[3]}\n')
+
+        pending = []
+        for start in range(0, len(img_paths), bs):
+            paths = img_paths[start:start + bs]
+            raws = [cv2.imread(path) for path in paths]   # BGR kept (no flip), models.py:153
+            self.engine.submit_u8(raws, reverse_channels=False)
+            pending.append((paths, raws))
+            if len(pending) == 2:
+                p0 = pending.pop(0)
+                write(p0[0], p0[1], self.engine.collect())
+        while pending:
+            p0 = pending.pop(0)
+            write(p0[0], p0[1], self.engine.collect())
