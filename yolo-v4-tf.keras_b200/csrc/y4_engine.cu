@@ -402,7 +402,12 @@ void launch_spp(y4_engine* e, int batch) {
     unsigned blocks = (unsigned)((total + 255) / 256);
     if (e->elt == 4) spp_kernel<float><<<blocks, 256, 0, e->stream>>>(p);
     else if (e->cfg.precision == Y4_PREC_FP16X3) spp_split_kernel<<<blocks, 256, 0, e->stream>>>(p, b.ptr_lo);
-    else if (e->cfg.precision == Y4_PREC_FP16 && e->spp_C % 8 == 0)
+    else if (e->cfg.precision == Y4_PREC_FP16 && e->spp_C % kSppChunk == 0 && (size_t)b.H * b.W * 256 <= 200 * 1024) {
+        const size_t smem = (size_t)b.H * b.W * 256;                    // x + three row-max tiles, 64 B per position each
+        static bool configured = false;
+        if (!configured) { cudaFuncSetAttribute(spp_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); configured = true; }
+        spp_sep_kernel<<<(unsigned)(batch * (e->spp_C / kSppChunk)), 256, smem, e->stream>>>(p);
+    } else if (e->cfg.precision == Y4_PREC_FP16 && e->spp_C % 8 == 0)
         spp_half8_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, e->stream>>>(p);
     else spp_kernel<__half><<<blocks, 256, 0, e->stream>>>(p);
     e->launches++;
