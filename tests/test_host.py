@@ -76,3 +76,30 @@ def test_preprocess_contract():
     img = (np.arange(30 * 50 * 3) % 256).astype(np.uint8).reshape(30, 50, 3)
     out = O.preprocess_img(img, 64)
     assert out.shape == (64, 64, 3) and out.dtype == np.float64 and 0 <= out.min() and out.max() <= 1
+
+
+def test_eval_map_matches_reference_golden(tmp_path):
+    """mAP evaluator vs golden results produced by running the reference's own eval_map / voc_ap source
+    (tests/golden/make_golden_map.py) on a seeded ground-truth / prediction folder with ties, duplicates, wrong classes."""
+    import json
+    import os
+    import y4b200
+    from y4b200.evaluate import eval_map, voc_ap
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'map_case.json')))
+    gt_dir, pr_dir, out_dir = tmp_path / 'gt', tmp_path / 'pred', tmp_path / 'out'
+    for d in (gt_dir, pr_dir, out_dir):
+        d.mkdir()
+    for k, v in g['files'].items():
+        (gt_dir / (k + '.txt')).write_text('\n'.join(v['gt']) + '\n')
+        (pr_dir / (k + '.txt')).write_text('\n'.join(v['pred']) + ('\n' if v['pred'] else ''))
+    res = eval_map(str(gt_dir), str(pr_dir), None, str(out_dir))
+    assert sorted(res['ap']) == g['classes_sorted']
+    for c, want in zip(g['classes_sorted'], g['ap_in_class_order']):
+        assert res['ap'][c] == pytest.approx(want, abs=1e-12), c
+    assert res['mAP'] == pytest.approx(g['mAP'], abs=1e-12)
+    assert (out_dir / 'output.txt').read_text() == g['output_txt']
+    for case in g['voc_ap_cases']:
+        ap, mrec, mpre = voc_ap(case['rec'], case['prec'])
+        assert ap == pytest.approx(case['ap'], abs=1e-15)
+        assert mrec == case['mrec'] and mpre == case['mpre']
+    assert y4b200.Yolov4.eval_map is not None

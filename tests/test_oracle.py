@@ -230,3 +230,69 @@ def test_resize_restatement_matches_cv2_live():
     for (h, w, S) in [(37, 53, 64), (333, 517, 416), (700, 300, 320), (64, 64, 608), (5, 9, 96)]:
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         assert np.array_equal(O.resize_linear_u8(img, S, S), cv2.resize(img, (S, S))), (h, w, S)
+
+
+# ---- the oracle vs the reference's OWN source (tests/golden/make_golden_refgraph.py) -------------------------------
+@pytest.fixture(scope='module')
+def refgraph():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'refgraph_416.npz'))
+
+
+def test_loader_matches_reference_load_weights(refgraph, weights):
+    """utils.py:12-53 executed from the reference's source on the synthetic darknet file: every array it hands to Keras
+    (HWIO kernel, head bias, [gamma, beta, mean, var]) equals what the oracle's loader parses, layer by layer."""
+    import hashlib
+    W, blob = weights
+    assert hashlib.sha256(blob).hexdigest() == str(refgraph['weights_sha256'])
+    P = O.Weights.from_darknet_bytes(blob)
+    want = dict(zip([str(k) for k in refgraph['loader_keys']], [str(v) for v in refgraph['loader_sha256']]))
+    assert len(want) == 110 + 107
+    for i, (o, p) in enumerate(zip(P.convs, P.p)):
+        h = hashlib.sha256(np.ascontiguousarray(p['w'], dtype=np.float32).tobytes())
+        if not o.bn:
+            h.update(np.ascontiguousarray(p['bias'], dtype=np.float32).tobytes())
+        assert h.hexdigest() == want[f'conv{i}'], i
+        if o.bn:
+            bn = np.stack([p['gamma'], p['beta'], p['mean'], p['var']]).astype(np.float32)
+            assert hashlib.sha256(bn.tobytes()).hexdigest() == want[f'bn{i}'], i
+
+
+def test_forward_matches_reference_graph(refgraph, weights):
+    """custom_layers.py:5-198 executed from the reference's source (eager numpy/torch stand-in for the Keras layers) at
+    416x416: the oracle's heads agree at 2,700 sampled positions and in their sums.  Pins conv order, concat order, SPP order,
+    add-after-activation, the asymmetric stride-2 padding and which convs are leaky / mish / linear."""
+    W, _ = weights
+    S = int(refgraph['img_size'])
+    heads = O.forward(O.synth_images(0, 0, 1, S), W)
+    for i, h in enumerate(heads):
+        idx, val, amax = refgraph[f'head{i}_idx'], refgraph[f'head{i}_val'], float(refgraph[f'head{i}_absmax'])
+        got = h.reshape(-1)[idx]
+        assert np.abs(got - val).max() <= 2e-4 * amax, (i, float(np.abs(got - val).max()), amax)
+        assert abs(float(h.astype(np.float64).sum()) - float(refgraph[f'head{i}_sum'])) <= 1e-5 * amax * h.size
+
+
+def test_decode_matches_reference_get_boxes_and_flattening(refgraph, weights):
+    """custom_layers.py:201-298 executed from the reference's source up to the TF NMS op.  (a) identical sparse heads in:
+    the tensors the reference passes to combined_non_max_suppression (boxes (N,1,4) / img_size, scores = conf * cls (N,80))
+    equal the oracle's, including the flat order n = off_scale + (row*g+col)*3 + a.  (b) the network's own heads: the 2,000
+    best (box, class) pairs and the candidate count above the threshold."""
+    W, _ = weights
+    S = int(refgraph['img_size'])
+    mo, mt, iou, thr = refgraph['nms_args']
+    assert (int(mo), int(mt)) == (O.MAX_BOXES, O.MAX_BOXES) and abs(iou - O.IOU_THRESHOLD) < 1e-7 and abs(thr - O.SCORE_THRESHOLD) < 1e-7
+    sparse = [refgraph[f'sparse_head{i}'] for i in range(3)]
+    boxes, scores = O.decode_heads(sparse, S)
+    assert boxes.shape == (1, 10647, 4) and scores.shape == (1, 10647, 80)
+    assert np.abs(boxes[0] - refgraph['b_nms_boxes']).max() <= 2e-6
+    nz = refgraph['b_nms_scores_nonzero_idx']
+    got_nz = np.nonzero(scores[0].reshape(-1) > 1e-4)[0]
+    assert np.array_equal(got_nz, nz)
+    assert np.abs(scores[0].reshape(-1)[nz] - refgraph['b_nms_scores_nonzero']).max() <= 1e-6
+    heads = O.forward(O.synth_images(0, 0, 1, S), W)
+    boxes, scores = O.decode_heads(heads, S)
+    flat = refgraph['a_top_flat']
+    assert np.abs(scores[0].reshape(-1)[flat] - refgraph['a_top_scores']).max() <= 2e-4
+    assert np.abs(boxes[0][flat // 80] - refgraph['a_top_boxes']).max() <= 2e-4
+    cnt = int((scores > O.SCORE_THRESHOLD).sum())
+    assert abs(cnt - int(refgraph['a_count_above_thr'])) <= 3, (cnt, int(refgraph['a_count_above_thr']))

@@ -135,3 +135,8 @@ class Yolov4(object):
         while pending:
             p0 = pending.pop(0)
             write(p0[0], p0[1], self.engine.collect())
+
+    def eval_map(self, gt_folder_path, pred_folder_path, temp_json_folder_path, output_files_path):
+        """models.py:182-507 without the per-detection JSON round trips and plots; same arguments, same output.txt."""
+        from .evaluate import eval_map
+        return eval_map(gt_folder_path, pred_folder_path, temp_json_folder_path, output_files_path)

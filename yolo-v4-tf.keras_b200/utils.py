@@ -6,6 +6,8 @@ draw_bbox(...)                     -> cv2 rectangles + labels; matplotlib only i
 """
 import numpy as np
 
+from .evaluate import voc_ap  # noqa: F401  (utils.py:311-356)
+
 
 def load_weights(model, weights_file_path):
     """`model` is a binding.Engine (the stand-in for the reference's Keras yolo_model).  The engine checks the
