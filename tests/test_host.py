@@ -103,3 +103,22 @@ def test_eval_map_matches_reference_golden(tmp_path):
         assert ap == pytest.approx(case['ap'], abs=1e-15)
         assert mrec == case['mrec'] and mpre == case['mpre']
     assert y4b200.Yolov4.eval_map is not None
+
+
+def test_get_detection_data_matches_reference_golden():
+    """utils.py:56-78 run from the reference's source (tests/golden/make_golden_detdata.py): same columns, dtypes, rows."""
+    import json
+    import os
+    from y4b200.utils import get_detection_data
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'detdata_case.json')))
+    n = g['n']
+    boxes = np.zeros((2, 100, 4), np.float32); boxes[0, :n] = np.array(g['boxes'], np.float32)
+    scores = np.zeros((2, 100), np.float32); scores[0, :n] = np.array(g['scores'], np.float32)
+    classes = np.zeros((2, 100), np.float32); classes[0, :n] = np.array(g['classes'], np.float32)
+    valid = np.array([n, 0], np.int32)
+    img = np.zeros(tuple(g['img_hw']) + (3,), np.uint8)
+    df = get_detection_data(img, [boxes, scores, classes, valid], g['names'])
+    assert list(df.columns) == g['columns']
+    assert [str(t) for t in df.dtypes] == g['dtypes']
+    rows = json.loads(df.to_json(orient='values'))
+    assert rows == g['rows']

@@ -704,7 +704,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         // (and therefore across GPUs, whatever each one picks).
         struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw, cta2; };
         std::vector<Cand> cands;
-        const bool allow_patch = !(getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '0');
+        const bool allow_patch = getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '1';    // A-patch plans: correct, never the fastest in context on B200
         const bool allow_bres = !(getenv("Y4_BRES") && getenv("Y4_BRES")[0] == '0');
         const int epi_mode = getenv("Y4_EPI") ? atoi(getenv("Y4_EPI")) : 1;     // 0 never, 1 autotune, 2 wherever eligible
         const int nepi_mode = getenv("Y4_NEPI") ? atoi(getenv("Y4_NEPI")) : 0;  // 4 / 8: only that many epilogue warps
