@@ -66,6 +66,8 @@ struct TcParams {
     // flat
     int Hp, Wp;                  // padded dims (same for in and out)
     long long M_total;           // batch * Hp * Wp
+    int m_start;                 // first row covered by a tile: Wp + 1, the first interior pixel (rows before it and after the last
+                                 // interior pixel are halo, stay zero and need no tile: 19x19 maps at batch 32 drop from 56 to 55 256-row tiles)
     // box
     int OH, OW, TH, TW, tiles_w, tiles_per_img;
     long long* dbg;              // optional per-CTA phase timestamps (y4_debug_trace_conv); nullptr in production
@@ -299,7 +301,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile) {
     t.n0 = (tile - mt * p.n_tiles) * BN;
     t.m0 = 0; t.img = 0; t.oh0 = 0; t.ow0 = 0;
     if (p.mode != 2) {
-        t.m0 = (long long)mt * 128;
+        t.m0 = (long long)p.m_start + (long long)mt * 128;
     } else {
         t.img = mt / p.tiles_per_img;
         const int r = mt - t.img * p.tiles_per_img;
@@ -945,7 +947,8 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
     long long m_tiles;
     if (pl.kind == 1) {
         pl.p.M_total = (long long)batch * pl.p.Hp * pl.p.Wp;
-        m_tiles = (pl.p.M_total + 127) / 128;
+        pl.p.m_start = pl.p.Wp + 1;
+        m_tiles = (pl.p.M_total - 2 * pl.p.m_start + 127) / 128;
     } else {
         m_tiles = (long long)batch * pl.p.tiles_per_img;
     }

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     pdl_wait();
 
     // cluster tile ct -> (256-row block, N tile); this CTA: rows +128*rank, weight rows +BN/2*rank
-    auto tile_m0 = [&](int ct) { return (long long)(ct / p.n_tiles) * 256 + 128 * (long long)rank; };
+    auto tile_m0 = [&](int ct) { return (long long)p.m_start + (long long)(ct / p.n_tiles) * 256 + 128 * (long long)rank; };
     auto tile_n0 = [&](int ct) { return (ct % p.n_tiles) * BN; };
 
     if (warp == 0) {
@@ -265,7 +265,8 @@ inline cudaError_t launch_tc2(const TcConvPlan& pl, dim3 grid, cudaStream_t st) 
 inline int tc2_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
     TcConvPlan pl = pl_in;
     pl.p.M_total = (long long)batch * pl.p.Hp * pl.p.Wp;
-    const long long m_tiles = (pl.p.M_total + 255) / 256;
+    pl.p.m_start = pl.p.Wp + 1;                                 // tiles start at the first interior pixel (see TcParams)
+    const long long m_tiles = (pl.p.M_total - 2 * pl.p.m_start + 255) / 256;
     pl.p.num_tiles = (int)(m_tiles * pl.p.n_tiles);
     const int max_clusters = sm_count() / 2;
     const int nclusters = pl.p.num_tiles < max_clusters ? pl.p.num_tiles : max_clusters;
