@@ -13,7 +13,8 @@
 //   * only the leader issues MMAs; tcgen05.commit multicasts the arrive to both CTAs' empty / tfull barriers;
 //   * the peer's epilogue warps arrive remotely on the leader's tempty barrier (mbarrier.arrive.shared::cluster);
 //   * TMEM is allocated with cta_group::2 by warp 1 of both CTAs; cluster barriers fence start-up and tear-down.
-// Flat mode (1x1 and 3x3 stride 1), 64-channel K blocks, fp16 in / fp16 out through the slab epilogue only.
+// Flat mode (1x1 and 3x3 stride 1; slab epilogue) and strided-box mode (3x3 stride 2: each CTA of the pair owns one TH x TW
+// output box, A comes from the four parity planes as in conv_tc.cuh, per-thread stores); 64-channel K blocks, fp16 in / out.
 #pragma once
 #include "conv_tc.cuh"
 
@@ -30,6 +31,11 @@ __device__ __forceinline__ void tma_load_2d_cg2(uint32_t dst, const CUtensorMap*
     asm volatile(
         "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_cg2(uint32_t dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void tmem_alloc_cg2(uint32_t dst_smem, uint32_t cols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
@@ -69,7 +75,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     const uint32_t base = (raw + 1023u) & ~1023u;
     const int S = p.stages, G = p.group;
     const uint32_t ring_bytes = (uint32_t)(S * G) * (uint32_t)STAGE_BYTES;
-    const uint32_t epi_bytes = epi_slab_bytes(NEPI, p.epi_gw);
+    const uint32_t epi_bytes = p.epi ? epi_slab_bytes(NEPI, p.epi_gw) : 0u;
     const uint32_t slabs = base + ring_bytes;
     const uint32_t bars = slabs + epi_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
@@ -84,7 +90,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmW);
         tma_prefetch_desc(&p.tmA[0]);
-        tma_prefetch_desc(&p.tmOut);
+        if (p.epi) tma_prefetch_desc(&p.tmOut);
+        if (p.mode == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
         for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 2 * NEPI); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -103,6 +110,18 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     // cluster tile ct -> (256-row block, N tile); this CTA: rows +128*rank, weight rows +BN/2*rank
     auto tile_m0 = [&](int ct) { return (long long)p.m_start + (long long)(ct / p.n_tiles) * 256 + 128 * (long long)rank; };
     auto tile_n0 = [&](int ct) { return (ct % p.n_tiles) * BN; };
+    // box mode: M tile index of this CTA (the odd CTA of the last pair may have none: it repeats the last tile and stores nothing)
+    const int m_tiles_box = p.mode == 2 ? (int)(p.M_total) : 0;                 // tc2_launch: batch * tiles_per_img
+    auto box_tile = [&](int ct, int& img, int& oh0, int& ow0) {
+        int mt = 2 * (ct / p.n_tiles) + (int)rank;
+        const bool real = mt < m_tiles_box;
+        if (!real) mt = m_tiles_box - 1;
+        img = mt / p.tiles_per_img;
+        const int r = mt - img * p.tiles_per_img;
+        const int th = r / p.tiles_w;
+        oh0 = th * p.TH; ow0 = (r - th * p.tiles_w) * p.TW;
+        return real;
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -110,20 +129,29 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
             for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters) {
                 const long long m0 = tile_m0(ct);
                 const int n0 = tile_n0(ct);
+                int bimg = 0, boh0 = 0, bow0 = 0;
+                if (p.mode == 2) box_tile(ct, bimg, boh0, bow0);
+                const uint32_t a_bytes = p.mode == 2 ? (uint32_t)(p.TH * p.TW * BK * 2) : (uint32_t)A_BYTES;
                 for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
                     const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
                     mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                     const uint32_t fb = (bar_full + 8u * s) & kPeerBitMask;          // the leader's barrier collects both CTAs' bytes
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
-                    if (rank == 0) mbar_expect_tx(bar_full + 8u * s, 2u * (uint32_t)gcount * (uint32_t)STAGE_BYTES);
+                    if (rank == 0) mbar_expect_tx(bar_full + 8u * s, 2u * (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES));
                     for (int kk = 0; kk < gcount; kk++) {
                         const int kb = kb0 + kk;
-                        int tap = 0, cb = kb;
-                        if (p.ksize == 3) { cb = kb / 9; tap = kb - cb * 9; }        // channel block outer, tap inner (as conv_tc.cuh)
-                        int shift = 0;
-                        if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
                         const uint32_t sa = base + (s * (uint32_t)G + (uint32_t)kk) * (uint32_t)STAGE_BYTES;
-                        tma_load_2d_cg2(sa, &p.tmA[0], fb, cb * BK, (int)(m0 + shift));
+                        int tap = 0, cb = kb;
+                        if (p.mode == 2) {                                            // box: tap outer (as conv_tc.cuh mode 2)
+                            tap = kb / p.kb_per_tap; cb = kb - tap * p.kb_per_tap;
+                            const int kh = tap / 3, kw = tap - kh * 3;
+                            tma_load_4d_cg2(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, cb * BK, bow0 + (kw >> 1), boh0 + (kh >> 1), bimg);
+                        } else {
+                            if (p.ksize == 3) { cb = kb / 9; tap = kb - cb * 9; }    // channel block outer, tap inner (as conv_tc.cuh)
+                            int shift = 0;
+                            if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
+                            tma_load_2d_cg2(sa, &p.tmA[0], fb, cb * BK, (int)(m0 + shift));
+                        }
                         tma_load_2d_cg2(sa + A_BYTES, &p.tmW, fb, (tap * p.kb_per_tap + cb) * BK, n0 + (int)rank * (BN / 2));
                     }
                 }
@@ -166,7 +194,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
         const bool gw64 = p.epi_gw == 64;
         const uint32_t slab_bytes = gw64 ? 2u * kSlabBytes : kSlabBytes;
         const uint32_t my_slabs = slabs + (uint32_t)(warp - 2) * 2u * slab_bytes;
-        if (has_res && cluster_id < p.num_tiles)
+        if (p.epi && has_res && cluster_id < p.num_tiles)
             res_prefetch(p, my_slabs, tile_m0(cluster_id) + q * 32, tile_n0(cluster_id) + 32 * set, lane, gw64);
         for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters, ti++) {
             const long long m0 = tile_m0(ct);
@@ -174,7 +202,15 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
             const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
             const long long pr = m0 + r;
             bool valid = pr < p.M_total;
-            {
+            long long drow = 0;
+            if (p.mode == 2) {
+                int bimg, boh0, bow0;
+                const bool real = box_tile(ct, bimg, boh0, bow0);
+                const int th = r / p.TW, tw = r - th * p.TW;
+                const int oh = boh0 + th, ow = bow0 + tw;
+                valid = real && (r < p.TH * p.TW) && oh < p.OH && ow < p.OW;
+                drow = ((long long)bimg * (p.OH + 2) + oh + 1) * (p.OW + 2) + ow + 1;
+            } else {
                 const unsigned up = (unsigned)(valid ? pr : 0);
                 const int wp = (int)(up % (unsigned)p.Wp);
                 const int hp = (int)((up / (unsigned)p.Wp) % (unsigned)p.Hp);
@@ -185,6 +221,26 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + as * (uint32_t)BN;
             uint32_t va[32];
             [[maybe_unused]] uint32_t vb[32];
+            if (p.mode == 2) {
+                // strided boxes: output rows are not consecutive in memory -> per-thread stores (conv_tc.cuh epilogue_chunk); NEPI == 4
+                if constexpr (NEPI == 4) {
+                    tmem_ld32_issue(tacc, va);
+#pragma unroll 1
+                    for (int c0 = 0; c0 < BN; c0 += 64) {
+                        tmem_ld_wait(va);
+                        tmem_ld32_issue(tacc + (uint32_t)(c0 + 32), vb);
+                        if (valid && n0 + c0 < p.cout_store) epilogue_chunk<false>(p, va, sbias, sbias, n0 + c0, drow, 0, 0, 0);
+                        __syncwarp();
+                        tmem_ld_wait(vb);
+                        if (c0 + 64 < BN) tmem_ld32_issue(tacc + (uint32_t)(c0 + 64), va);
+                        if (valid && n0 + c0 + 32 < p.cout_store) epilogue_chunk<false>(p, vb, sbias, sbias, n0 + c0 + 32, drow, 0, 0, 0);
+                        __syncwarp();
+                    }
+                    tc_fence_before();
+                    if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * as);
+                }
+                continue;
+            }
             auto do_group = [&](const uint32_t (&v)[32], int k) {
                 if (n0 + 32 * k >= p.cout_store) return;
                 const int h = gw64 ? (k & 1) : 0;
@@ -234,7 +290,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                 }
             }
         }
-        if (lane == 0) bulk_wait_all();
+        if (p.epi && lane == 0) bulk_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -264,9 +320,15 @@ inline cudaError_t launch_tc2(const TcConvPlan& pl, dim3 grid, cudaStream_t st) 
 // launch of a cta2 plan (tc_plan2): one cluster per SM pair
 inline int tc2_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
     TcConvPlan pl = pl_in;
-    pl.p.M_total = (long long)batch * pl.p.Hp * pl.p.Wp;
-    pl.p.m_start = pl.p.Wp + 1;                                 // tiles start at the first interior pixel (see TcParams)
-    const long long m_tiles = (pl.p.M_total - 2 * pl.p.m_start + 255) / 256;
+    long long m_tiles;
+    if (pl.kind == 2) {
+        pl.p.M_total = (long long)batch * pl.p.tiles_per_img;   // box mode: number of 128-row M tiles (two per cluster tile)
+        m_tiles = (pl.p.M_total + 1) / 2;
+    } else {
+        pl.p.M_total = (long long)batch * pl.p.Hp * pl.p.Wp;
+        pl.p.m_start = pl.p.Wp + 1;                             // tiles start at the first interior pixel (see TcParams)
+        m_tiles = (pl.p.M_total - 2 * pl.p.m_start + 255) / 256;
+    }
     pl.p.num_tiles = (int)(m_tiles * pl.p.n_tiles);
     const int max_clusters = sm_count() / 2;
     const int nclusters = pl.p.num_tiles < max_clusters ? pl.p.num_tiles : max_clusters;
@@ -288,15 +350,18 @@ inline int tc2_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
     return e == cudaSuccess ? 0 : -1;
 }
 
-// Plan for the CTA-pair kernel; returns 1 when the layer is eligible (flat mode, 64-channel K blocks, fp16 slab epilogue).
+// Plan for the CTA-pair kernel; returns the kernel kind (1 flat, 2 strided box) when the layer is eligible, 0 otherwise.
 inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn, int smem_budget_kb, int group, int nepi, int gw) {
-    if (d.raw_in || d.cin % 64 != 0 || d.stride != 1 || d.split || d.out_f32 || d.upsample) return 0;
-    if (d.cout_pad % bn || d.cout % gw != 0 || (gw != 32 && (gw != 64 || nepi != 4)) || (nepi != 4 && nepi != 8)) return 0;
+    if (d.raw_in || d.cin % 64 != 0 || d.split || d.out_f32 || d.upsample) return 0;
+    const bool box = d.stride == 2;
+    if (box ? (d.k != 3 || nepi != 4 || gw != 32) : (d.stride != 1)) return 0;
+    if (d.cout_pad % bn || (nepi != 4 && nepi != 8)) return 0;
+    if (!box && (d.cout % gw != 0 || (gw != 32 && (gw != 64 || nepi != 4)))) return 0;
     TcConvPlan P;
     TcParams& p = P.p;
     memset(&p, 0, sizeof(p));
-    P.tile_n = bn; P.bk = 64; P.kind = 1; P.nepi = nepi; P.cta2 = 1; P.ctas_per_sm = 1;
-    p.mode = 1; p.epi = 1; p.epi_gw = gw;
+    P.tile_n = bn; P.bk = 64; P.kind = box ? 2 : 1; P.nepi = nepi; P.cta2 = 1; P.ctas_per_sm = 1;
+    p.mode = box ? 2 : 1; p.epi = box ? 0 : 1; p.epi_gw = gw;
     p.bias = d.bias; p.out = d.out; p.res = reinterpret_cast<const __half*>(d.res);
     p.act_scale = 1.f; p.inv_act_scale = 1.f;
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
@@ -315,26 +380,45 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     {
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d.cout_pad};
         cuuint64_t str[1] = {(cuuint64_t)K * 2};
-        cuuint32_t box[2] = {64, (cuuint32_t)(bn / 2)};
-        if (!encode_map(&p.tmW, const_cast<__half*>(d.w16), 2, dims, str, box, 128, err)) return -1;
+        cuuint32_t box2[2] = {64, (cuuint32_t)(bn / 2)};
+        if (!encode_map(&p.tmW, const_cast<__half*>(d.w16), 2, dims, str, box2, 128, err)) return -1;
     }
-    {
+    if (!box) {
         cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)p.rows_alloc};
         cuuint64_t str[1] = {(cuuint64_t)d.in_ld * 2};
-        cuuint32_t box[2] = {64, 128};
-        if (!encode_map(&p.tmA[0], in_base, 2, dims, str, box, 128, err)) return -1;
-    }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)p.cout_store, (cuuint64_t)p.rows_alloc};
-        cuuint64_t str[1] = {(cuuint64_t)d.out_ld * 2};
-        cuuint32_t box[2] = {(cuuint32_t)gw, 32};
+        cuuint32_t box2[2] = {64, 128};
+        if (!encode_map(&p.tmA[0], in_base, 2, dims, str, box2, 128, err)) return -1;
+        cuuint64_t odims[2] = {(cuuint64_t)p.cout_store, (cuuint64_t)p.rows_alloc};
+        cuuint64_t ostr[1] = {(cuuint64_t)d.out_ld * 2};
+        cuuint32_t obox[2] = {(cuuint32_t)gw, 32};
         char* out_base = reinterpret_cast<char*>(d.out) + (size_t)d.out_choff * 2;
-        if (!encode_map(&p.tmOut, out_base, 2, dims, str, box, gw * 2, err)) return -1;
+        if (!encode_map(&p.tmOut, out_base, 2, odims, ostr, obox, gw * 2, err)) return -1;
+    } else {
+        // output box TH x TW per CTA (<= 128 pixels), chosen for the most useful rows per tile; four parity-plane views of the input
+        p.OH = d.OH; p.OW = d.OH;
+        int bestTW = 1, bestTH = 1; double best = -1;
+        for (int tw = 1; tw <= d.OH && tw <= 128; tw++)
+            for (int th = 1; th * tw <= 128 && th <= d.OH; th++) {
+                const long long tiles = (long long)((d.OH + tw - 1) / tw) * ((d.OH + th - 1) / th);
+                const double eff = (double)d.OH * d.OH / (tiles * 128.0);
+                if (eff > best + 1e-9) { best = eff; bestTW = tw; bestTH = th; }
+            }
+        p.TW = bestTW; p.TH = bestTH;
+        p.tiles_w = (d.OH + bestTW - 1) / bestTW;
+        p.tiles_per_img = p.tiles_w * ((d.OH + bestTH - 1) / bestTH);
+        for (int ph = 0; ph < 2; ph++)
+            for (int pw = 0; pw < 2; pw++) {
+                char* b = in_base + ((size_t)ph * in_Wp + pw) * d.in_ld * 2;
+                cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)in_Wp / 2, (cuuint64_t)in_Hp / 2, (cuuint64_t)d.max_batch};
+                cuuint64_t str[3] = {(cuuint64_t)2 * d.in_ld * 2, (cuuint64_t)2 * in_Wp * d.in_ld * 2, (cuuint64_t)in_Hp * in_Wp * d.in_ld * 2};
+                cuuint32_t box4[4] = {64, (cuuint32_t)bestTW, (cuuint32_t)bestTH, 1};
+                if (!encode_map(&p.tmA[ph * 2 + pw], b, 4, dims, str, box4, 128, err)) return -1;
+            }
     }
     if (group < 1) group = 1;
     if (group > p.num_kb) group = p.num_kb;
     p.group = group;
-    const size_t epi_bytes = epi_slab_bytes(nepi, gw);
+    const size_t epi_bytes = box ? 0 : epi_slab_bytes(nepi, gw);
     const size_t stage_bytes = ((size_t)128 * 64 * 2 + (size_t)(bn / 2) * 64 * 2) * group;
     const size_t fixed = 1024 + epi_bytes + 16 * 8 + 192 + 4 * (size_t)d.cout_pad;
     const size_t budget = (size_t)smem_budget_kb * 1024;
@@ -347,7 +431,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     P.smem = 1024 + S * stage_bytes + epi_bytes + 16 * S + 192 + 4 * (size_t)p.bias_n;
     if (P.smem > 225 * 1024) return 0;
     *pl = P;
-    return 1;
+    return P.kind;
 }
 
 }  // namespace y4

@@ -758,7 +758,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                     const Cand& cd = cands[ci];
                     if (!cd.epi && epi_mode == 2 && best[li].p.epi) continue;
                     std::string er2;
-                    if (cd.cta2) { if (c.kind != 1 || tc_plan2(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.group, cd.nepi, cd.gw) != 1) continue; }
+                    if (cd.cta2) { if (tc_plan2(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.group, cd.nepi, cd.gw) != c.kind) continue; }
                     else if (tc_plan(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw) != c.kind) continue;
                     has[li] = 1; any = true;
                 }
