@@ -12,11 +12,16 @@
 //     (h%2, w%2); tap (kh,kw) of an output box TH x TW is a dense 4-D TMA box of plane (kh&1, kw&1) at
 //     (ow0 + (kw>>1), oh0 + (kh>>1)).  Four 4-D tensor maps per input tensor.
 //
-// CTA = 6 warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc/free), warps 2..5 epilogue
-// (TMEM -> registers -> bias + activation (+ residual) -> fp16/fp32 global stores, halo rows skipped,
-// optional 2x2 replicated store = fused UpSampling2D).  PERSISTENT: each CTA loops over 128 x BN output tiles
-// (tile = blockIdx.x, += gridDim.x); the smem ring keeps running across tiles and TMEM holds TWO accumulator
-// stages, so the MMAs of tile i+1 overlap the epilogue of tile i and the per-tile start-up latency is paid once.
+// CTA = 2 + NEPI warps: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc/free), NEPI (4 or 8) epilogue warps
+// (TMEM -> registers -> bias + activation (+ residual) -> fp16).  Two epilogues:
+//   * slab epilogue (epi = 1): each warp packs its 32 rows into a TMA-swizzled shared-memory slab and one lane issues a TMA box
+//     store; the skip tensor arrives in the slab by coalesced cp.async; halo rows are stored as zeros.  With NEPI = 8 two warps
+//     share a TMEM lane quarter and alternate 32-column groups (lean loop, 96 registers, two 320-thread CTAs per SM);
+//   * per-thread global stores (epi = 0): halo rows skipped, optional 2x2 replicated store (fused UpSampling2D), fp32 heads.
+// PERSISTENT: each CTA loops over 128 x BN output tiles (tile = blockIdx.x, += gridDim.x); the smem ring keeps running
+// across tiles and TMEM holds TWO accumulator stages, so the MMAs of tile i+1 overlap the epilogue of tile i.
+// Optional: the whole weight matrix resident in shared memory (bres, one N tile), A-patch reuse (mode 3, opt-in).
+// The CTA-pair variant (tcgen05.mma.cta_group::2) lives in conv_tc2.cuh and shares the helpers below.
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>
@@ -992,7 +997,8 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     if (d.split && (patch || bk != 64 && bk != 32)) return 0;
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
     p.act = d.act; p.out_f32 = d.out_f32; p.upsample = d.upsample;
-    if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);      // timing experiments only (wrong results)
+    if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);
+    if (getenv("Y4_DEBUG_NORES")) p.res = nullptr;                          // timing experiments only (wrong results)
     p.cout_store = d.out_f32 ? d.cout_pad : d.cout;
     p.ksize = d.k;
     p.kb_per_tap = d.cin / bk;

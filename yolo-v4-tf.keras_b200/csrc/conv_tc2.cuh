@@ -367,6 +367,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
     p.act = d.act;
     if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);
+    if (getenv("Y4_DEBUG_NORES")) p.res = nullptr;                          // timing experiments only (wrong results)
     p.cout_store = d.cout;
     p.ksize = d.k;
     p.kb_per_tap = d.cin / 64;
