@@ -213,8 +213,9 @@ def main():
             continue
         l = layers[li]; li += 1
         if l['kernel_kind'] in (1, 2):
-            name = (f"conv_tc2_kernel<{l['tile_n']}, {l['tc_epi_warps']}>" if l['tc_mode'] == 4
-                    else f"conv_tc_kernel<{l['tile_n']}, {l['tc_bk']}, 0, {l['tc_epi_warps']}>")
+            nepi, lean = (4, 1) if l['tc_epi_warps'] == 44 else (l['tc_epi_warps'], 0)
+            name = (f"conv_tc2_kernel<{l['tile_n']}, {nepi}>" if l['tc_mode'] == 4
+                    else f"conv_tc_kernel<{l['tile_n']}, {l['tc_bk']}, 0, {nepi}, {lean}>")
         else:
             name = {4: 'conv0_tc_kernel', 3: 'conv0_direct_kernel', 0: 'conv_simt_kernel'}.get(l['kernel_kind'], 'other')
         g = groups.setdefault(name, [0, 0.0, 0.0])

@@ -17,7 +17,11 @@ scale = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 
 
 def label(name):
     name = re.sub(r'^void ', '', name)
-    return re.sub(r'\(.*$', '', name)
+    name = re.sub(r'\(.*$', '', name)
+    m = re.match(r'conv_tc_kernel<(\d+), (\d+), (\d+), (\d+)(?:, (\d+))?>', name)     # default template argument LEAN = 0 is not printed
+    if m:
+        name = f'conv_tc_kernel<{m.group(1)}, {m.group(2)}, {m.group(3)}, {m.group(4)}, {m.group(5) or 0}>'
+    return name
 
 
 per = collections.defaultdict(lambda: collections.defaultdict(dict))     # kernel -> launch id -> metric -> value

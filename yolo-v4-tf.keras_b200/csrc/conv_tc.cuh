@@ -82,6 +82,7 @@ struct TcConvPlan {
     TcParams p;
     int kind = 0;                // 1 flat, 2 box
     int tile_n = 0, bk = 64, stages = 0, ctas_per_sm = 1, nepi = 4;
+    int lean = 0;                // 1: lean 4-warp epilogue compiled for four CTAs per SM (BN = 64, slab epilogue)
     int cta2 = 0;                // 1: CTA-pair kernel (conv_tc2.cuh), 256-row tiles, tcgen05.mma.cta_group::2
     size_t smem = 0;
     int in_Hp = 0, in_Wp = 0;
@@ -482,9 +483,12 @@ __device__ __forceinline__ void epi_group(const TcParams& p, const uint32_t (&v)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-template <int BN, int BK, bool SPLIT, int NEPI>
-__global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : 2) conv_tc_kernel(const __grid_constant__ TcParams p) {
+// LEAN (NEPI = 4, BN = 64): the single-buffer epilogue loop compiled for FOUR 192-thread CTAs per SM (<= 85 registers):
+// as many epilogue warps per SM as two 8-warp CTAs, but four independent tile pipelines.
+template <int BN, int BK, bool SPLIT, int NEPI, bool LEAN = false>
+__global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) conv_tc_kernel(const __grid_constant__ TcParams p) {
     static_assert(NEPI == 4 || (NEPI == 8 && !SPLIT), "8 epilogue warps: slab epilogue only");
+    static_assert(!LEAN || (NEPI == 4 && !SPLIT && BN == 64), "lean 4-CTA/SM variant: 64-wide tiles, slab epilogue only");
     constexpr int SWZ = BK * 2;
     constexpr int A_BYTES = 128 * BK * 2;
     constexpr int B_BYTES = BN * BK * 2;
@@ -823,7 +827,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : 2) conv_tc_kernel(
                     sit++;
                 };
                 auto release_acc = [&]() { tc_fence_before(); if (lane == 0) mbar_arrive(bar_tempty + 8u * as); };
-                if constexpr (NEPI == 8) {
+                if constexpr (NEPI == 8 || LEAN) {
                     // lean loop (fits two 320-thread CTAs per SM): one register buffer, no software pipelining of the TMEM
                     // loads -- sixteen epilogue warps per SM hide that latency by switching warps instead
 #pragma unroll 1
@@ -856,7 +860,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : 2) conv_tc_kernel(
                 continue;
                 }
             }
-            if constexpr (NEPI == 4) {
+            if constexpr (NEPI == 4 && !LEAN) {
             tmem_ld32_issue(tacc, va);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 64) {
@@ -919,11 +923,11 @@ inline bool pdl_enabled() {
     return on;
 }
 
-template <int BN, int BK, bool SPLIT, int NEPI>
+template <int BN, int BK, bool SPLIT, int NEPI, bool LEAN = false>
 inline cudaError_t launch_inst2(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, SPLIT, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
+        cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, SPLIT, NEPI, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -933,11 +937,12 @@ inline cudaError_t launch_inst2(const TcConvPlan& pl, dim3 grid, cudaStream_t st
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, BK, SPLIT, NEPI>, pl.p);
+    return cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, BK, SPLIT, NEPI, LEAN>, pl.p);
 }
 template <int BN, int BK>
 inline cudaError_t launch_inst(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
     if (pl.p.split) return launch_inst2<BN, BK, true, 4>(pl, grid, st);
+    if constexpr (BN == 64) { if (pl.lean) return launch_inst2<BN, BK, false, 4, true>(pl, grid, st); }
     return pl.nepi == 8 ? launch_inst2<BN, BK, false, 8>(pl, grid, st) : launch_inst2<BN, BK, false, 4>(pl, grid, st);
 }
 
@@ -978,7 +983,7 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 
 // returns kernel kind (0 = not eligible -> CUDA-core kernel, 1 = flat GEMM, 2 = strided box), <0 on error
 inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0, int group = 1,
-                   int epi = 0, int nepi = 4, int bres = 0, int gw = 32) {
+                   int epi = 0, int nepi = 4, int bres = 0, int gw = 32, int lean = 0) {
     if (d.raw_in) return 0;                                   // conv 0 (cin = 3): CUDA-core kernel
     const int bk = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 0);
     if (!bk) return 0;
@@ -1056,7 +1061,8 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     }
     size_t epi_bytes = 0;
     if (nepi != 4 && (nepi != 8 || !epi)) return 0;
-    P.nepi = nepi;
+    if (lean && (!epi || nepi != 4 || bn != 64 || d.split)) return 0;
+    P.nepi = nepi; P.lean = lean;
     if (epi) {
         // slab epilogue: flat tiles, fp16 output written in place (no upsample), whole 32- or 64-channel groups
         if (P.kind != 1 || d.out_f32 || d.upsample || d.split || p.cout_store % gw != 0) return 0;
@@ -1132,7 +1138,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     int cps = (int)((227 * 1024) / (P.smem + 1024));            // +1 KB: per-CTA reserved shared memory
     const int tmem_cols = 2 * bn;
     if (cps > 512 / tmem_cols) cps = 512 / tmem_cols;            // two accumulator stages per CTA must all fit in TMEM
-    if (cps > 2) cps = 2;                                        // register file: 168 regs x 192 threads
+    if (cps > (lean ? 4 : 2)) cps = lean ? 4 : 2;                // register file: 168 regs x 192 threads (85 for the lean variant)
     if (cps < 1) cps = 1;
     if (d.split) cps = 1;                                       // split kernels use > 170 registers/thread
     P.ctas_per_sm = cps;

@@ -702,7 +702,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         // barrier x {A-patch reuse, resident weights} x epilogue {per-thread stores, slab + TMA store with 4 or 8 warps}.
         // Every candidate accumulates K in the same order and rounds once, so outputs are bit-identical across them
         // (and therefore across GPUs, whatever each one picks).
-        struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw, cta2; };
+        struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw, cta2, lean; };
         std::vector<Cand> cands;
         const bool allow_patch = getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '1';    // A-patch plans: correct, never the fastest in context on B200
         const bool allow_bres = !(getenv("Y4_BRES") && getenv("Y4_BRES")[0] == '0');
@@ -710,7 +710,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         const int nepi_mode = getenv("Y4_NEPI") ? atoi(getenv("Y4_NEPI")) : 0;  // 4 / 8: only that many epilogue warps
         const int gw_mode = getenv("Y4_GW") ? atoi(getenv("Y4_GW")) : 0;        // 32 / 64: only that slab group width
         if (const char* f = getenv("Y4_FORCE")) {                                 // "bn,kb,patch,group,epi,nepi,bres,gw": that plan wherever it applies
-            Cand cd{}; if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d", &cd.bn, &cd.kb, &cd.patch, &cd.group, &cd.epi, &cd.nepi, &cd.bres, &cd.gw, &cd.cta2) >= 8) cands.push_back(cd);
+            Cand cd{}; if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", &cd.bn, &cd.kb, &cd.patch, &cd.group, &cd.epi, &cd.nepi, &cd.bres, &cd.gw, &cd.cta2, &cd.lean) >= 8) cands.push_back(cd);
         } else {
             static const bool allow_cta2 = !(getenv("Y4_CTA2") && getenv("Y4_CTA2")[0] == '0');
             if (allow_cta2)                                                      // CTA-pair kernel: {N tile, k-blocks per barrier, epilogue warps, group width}
@@ -718,6 +718,9 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                     for (int g : {1, 2, 3})
                         for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}})
                             cands.push_back({bn, 224, 0, g, 1, ep.first, 0, ep.second, 1});
+            for (int bres = 0; bres <= (allow_bres ? 1 : 0); bres++)            // lean 4-warp epilogue, four CTAs per SM (64-wide tiles)
+                for (int gw : {32, 64})
+                    for (int kb : {56, 75}) cands.push_back({64, kb, 0, 1, 1, 4, bres, gw, 0, 1});
             // {epilogue, epilogue warps, group width}
             const int epis[][3] = {{1, 4, 64}, {1, 4, 32}, {1, 8, 32}, {0, 4, 32}};
             for (int bn : {64, 128, 256})
@@ -759,7 +762,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                     if (!cd.epi && epi_mode == 2 && best[li].p.epi) continue;
                     std::string er2;
                     if (cd.cta2) { if (tc_plan2(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.group, cd.nepi, cd.gw) != c.kind) continue; }
-                    else if (tc_plan(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw) != c.kind) continue;
+                    else if (tc_plan(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw, cd.lean) != c.kind) continue;
                     has[li] = 1; any = true;
                 }
                 if (!any) continue;
@@ -1178,7 +1181,7 @@ int y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info) {
     const bool tc = c.kind == 1 || c.kind == 2;
     info->tc_mode = tc ? (c.tc.cta2 ? 4 : c.tc.p.mode) : 0; info->tc_epilogue = tc && c.tc.p.epi ? c.tc.p.epi_gw : 0; info->tc_stages = tc ? c.tc.stages : 0;
     info->tc_group = tc ? c.tc.p.group : 0; info->tc_ctas_per_sm = tc ? c.tc.ctas_per_sm : 0; info->tc_bk = tc ? c.tc.bk : 0;
-    info->tc_epi_warps = tc ? c.tc.nepi : 0; info->tc_resident_w = tc ? c.tc.p.bres : 0;
+    info->tc_epi_warps = tc ? (c.tc.lean ? 44 : c.tc.nepi) : 0; info->tc_resident_w = tc ? c.tc.p.bres : 0;
     return Y4_OK;
 }
 
