@@ -37,6 +37,9 @@ struct TcConvDesc {
     void* out; int out_ld, out_choff, out_f32, upsample;
     const void* res; int res_ld, res_choff;
     const __half* w16; const float* bias;
+    // pixel-pair view for a 3x3 stride-2 conv with cin = 32 (conv 1): two neighbouring pixels = 64 contiguous channels, so the taps
+    // (kh, kw=0|1) are ONE 128 B-row box and (kh, kw=2|zero) another: 6 taps of 64 instead of 9 of 32 (w16_pair: [cout_pad][6*64])
+    int pairx; const __half* w16_pair;
     // split precision (Y4_PREC_FP16X3): low-order fp16 planes of activations / weights, per-cout power-of-two weight scale
     int split; const void* in_lo; void* out_lo; const void* res_lo; const __half* w16_lo; const float* wscale;
 };
@@ -75,6 +78,7 @@ struct TcParams {
                                  // interior pixel are halo, stay zero and need no tile: 19x19 maps at batch 32 drop from 56 to 55 256-row tiles)
     // box
     int OH, OW, TH, TW, tiles_w, tiles_per_img;
+    int pairx;                   // box mode over the pixel-pair view: tap t = (kh, j): plane (kh & 1, 0), x offset j, y offset kh >> 1
     long long* dbg;              // optional per-CTA phase timestamps (y4_debug_trace_conv); nullptr in production
 };
 
@@ -454,6 +458,15 @@ __device__ __forceinline__ void epi_group(const TcParams& p, const uint32_t (&v)
     if (p.act == 2) act32_fast<2>(v, sb, f);
     else if (p.act == 1) act32_fast<1>(v, sb, f);
     else act32_fast<0>(v, sb, f);
+    if (p.out_f32) {                                        // fp32 heads: 32 columns = one 128 B slab row (SWIZZLE_128B), no skip tensor
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            uint4 o = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]), __float_as_uint(f[4 * j + 3]));
+            if (!interior) o = make_uint4(0u, 0u, 0u, 0u);
+            sts128(slab_chunk_addr(slab, lane, j, true), o);
+        }
+        return;
+    }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const uint32_t addr = slab_chunk_addr(slab, lane, 4 * h + j, gw64);
@@ -513,7 +526,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                                             : wres_bytes + (uint32_t)(S * G) * ASTRIDE;
     const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);      // mode 3: first B stage, or the resident W
     const uint32_t wres = p.mode == 3 ? bring : base;                              // resident W blocks, in K order
-    const uint32_t epi_bytes = (!SPLIT && p.epi) ? epi_slab_bytes(NEPI, p.epi_gw) : 0u;   // 1024 B aligned: ring_bytes is a multiple of 1024
+    const uint32_t epi_bytes = (!SPLIT && p.epi) ? epi_slab_bytes(NEPI, p.out_f32 ? 64 : p.epi_gw) : 0u;   // 1024 B aligned: ring_bytes is a multiple of 1024
     const uint32_t slabs = base + ring_bytes;
     const uint32_t bars = slabs + epi_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
@@ -651,6 +664,9 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                             int shift = 0;
                             if (p.ksize == 3) { const int kh = tap / 3, kw = tap - kh * 3; shift = (kh - 1) * p.Wp + (kw - 1); }
                             tma_load_2d(sa, &p.tmA[0], fb, c0, (int)(tc.m0 + shift));
+                        } else if (p.pairx) {
+                            const int kh = tap >> 1, j = tap & 1;
+                            tma_load_4d(sa, &p.tmA[(kh & 1) * 2], fb, c0, tc.ow0 + j, tc.oh0 + (kh >> 1), tc.img);
                         } else {
                             const int kh = tap / 3, kw = tap - kh * 3;
                             tma_load_4d(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, c0, tc.ow0 + (kw >> 1), tc.oh0 + (kh >> 1), tc.img);
@@ -765,8 +781,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
         uint32_t ti = 0, sit = 0;                           // sit: slab groups issued by this warp (epi = 1)
         const bool slab_epi = !SPLIT && p.epi;
         const bool has_res = p.res != nullptr;
-        const bool gw64 = p.epi_gw == 64;                   // 64-channel groups: NEPI == 4 only (host)
-        const uint32_t slab_bytes = gw64 ? 2u * kSlabBytes : kSlabBytes;
+        const bool gw64 = p.epi_gw == 64 && !p.out_f32;     // 64-channel groups: NEPI == 4 only (host)
+        const uint32_t slab_bytes = (gw64 || p.out_f32) ? 2u * kSlabBytes : kSlabBytes;     // fp32 heads: 32 columns x 4 B = 128 B rows
         const uint32_t my_slabs = slabs + (uint32_t)(warp - 2) * 2u * slab_bytes;
         if (slab_epi && has_res && (int)blockIdx.x < p.num_tiles) {
             const TileCoord t0 = decode_tile<BN>(p, (int)blockIdx.x);
@@ -907,11 +923,11 @@ inline PFN_encodeTiled get_encode_fn() {
 }
 
 inline bool encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                       const cuuint32_t* box, int swz_bytes, std::string* err) {
+                       const cuuint32_t* box, int swz_bytes, std::string* err, bool f32 = false) {
     PFN_encodeTiled fn = get_encode_fn();
     if (!fn) { *err = "cuTensorMapEncodeTiled entry point not found"; return false; }
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, es,
+    CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swz_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r); return false; }
@@ -985,7 +1001,10 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0, int group = 1,
                    int epi = 0, int nepi = 4, int bres = 0, int gw = 32, int lean = 0) {
     if (d.raw_in) return 0;                                   // conv 0 (cin = 3): CUDA-core kernel
-    const int bk = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 0);
+    if (d.pairx && (d.cin != 32 || d.stride != 2 || d.k != 3 || d.split || !d.w16_pair || d.in_ld != 32 || d.in_choff != 0)) return 0;
+    const int cin = d.pairx ? 64 : d.cin;                     // pixel-pair view: 64 channels per (pair) pixel
+    const int ntaps = d.pairx ? 6 : d.k * d.k;
+    const int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 0);
     if (!bk) return 0;
     if (d.upsample && d.out_f32) return 0;
     int bn = d.cout_pad >= 128 ? 128 : 64;
@@ -1006,9 +1025,10 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     if (getenv("Y4_DEBUG_NORES")) p.res = nullptr;                          // timing experiments only (wrong results)
     p.cout_store = d.out_f32 ? d.cout_pad : d.cout;
     p.ksize = d.k;
-    p.kb_per_tap = d.cin / bk;
-    p.num_kb = d.k * d.k * p.kb_per_tap;
-    const int K = d.k * d.k * d.cin;
+    p.kb_per_tap = cin / bk;
+    p.num_kb = ntaps * p.kb_per_tap;
+    p.pairx = d.pairx;
+    const int K = ntaps * cin;
     const int swz = bk * 2;
     const int in_Hp = d.in_H + 2, in_Wp = d.in_H + 2;
     P.in_Hp = in_Hp; P.in_Wp = in_Wp;
@@ -1019,7 +1039,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d.cout_pad};
         cuuint64_t str[1] = {(cuuint64_t)K * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)bn};
-        if (!encode_map(&p.tmW, const_cast<__half*>(d.w16), 2, dims, str, box, swz, err)) return -1;
+        if (!encode_map(&p.tmW, const_cast<__half*>(d.pairx ? d.w16_pair : d.w16), 2, dims, str, box, swz, err)) return -1;
         if (d.split && !encode_map(&p.tmW_lo, const_cast<__half*>(d.w16_lo), 2, dims, str, box, swz, err)) return -1;
     }
     if (d.stride == 1) {
@@ -1049,7 +1069,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
         for (int ph = 0; ph < 2; ph++)
             for (int pw = 0; pw < 2; pw++) {
                 char* b = in_base + ((size_t)ph * in_Wp + pw) * d.in_ld * 2;
-                cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)in_Wp / 2, (cuuint64_t)in_Hp / 2, (cuuint64_t)d.max_batch};
+                cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)in_Wp / 2, (cuuint64_t)in_Hp / 2, (cuuint64_t)d.max_batch};
                 cuuint64_t str[3] = {(cuuint64_t)2 * d.in_ld * 2, (cuuint64_t)2 * in_Wp * d.in_ld * 2, (cuuint64_t)in_Hp * in_Wp * d.in_ld * 2};
                 cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)bestTW, (cuuint32_t)bestTH, 1};
                 if (!encode_map(&p.tmA[ph * 2 + pw], b, 4, dims, str, box, swz, err)) return -1;
@@ -1065,16 +1085,18 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     P.nepi = nepi; P.lean = lean;
     if (epi) {
         // slab epilogue: flat tiles, fp16 output written in place (no upsample), whole 32- or 64-channel groups
-        if (P.kind != 1 || d.out_f32 || d.upsample || d.split || p.cout_store % gw != 0) return 0;
+        if (P.kind != 1 || d.upsample || d.split || p.cout_store % gw != 0) return 0;
         if (gw != 32 && (gw != 64 || nepi != 4)) return 0;
+        if (d.out_f32 && (gw != 32 || d.res)) return 0;            // fp32 heads: 32-column groups (128 B slab rows), no skip tensor
         p.epi = 1; p.epi_gw = gw;
         p.rows_alloc = (long long)d.max_batch * in_Hp * in_Wp;
+        const int esz = d.out_f32 ? 4 : 2;
         cuuint64_t dims[2] = {(cuuint64_t)p.cout_store, (cuuint64_t)p.rows_alloc};
-        cuuint64_t str[1] = {(cuuint64_t)d.out_ld * 2};
+        cuuint64_t str[1] = {(cuuint64_t)d.out_ld * esz};
         cuuint32_t box[2] = {(cuuint32_t)gw, 32};
-        char* out_base = reinterpret_cast<char*>(d.out) + (size_t)d.out_choff * 2;
-        if (!encode_map(&p.tmOut, out_base, 2, dims, str, box, gw * 2, err)) return -1;
-        epi_bytes = epi_slab_bytes(nepi, gw);
+        char* out_base = reinterpret_cast<char*>(d.out) + (size_t)d.out_choff * esz;
+        if (!encode_map(&p.tmOut, out_base, 2, dims, str, box, gw * esz, err, d.out_f32 != 0)) return -1;
+        epi_bytes = epi_slab_bytes(nepi, d.out_f32 ? 64 : gw);
     }
     size_t wres_bytes = 0;
     if (bres) {

@@ -144,8 +144,13 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                         int tap = 0, cb = kb;
                         if (p.mode == 2) {                                            // box: tap outer (as conv_tc.cuh mode 2)
                             tap = kb / p.kb_per_tap; cb = kb - tap * p.kb_per_tap;
-                            const int kh = tap / 3, kw = tap - kh * 3;
-                            tma_load_4d_cg2(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, cb * BK, bow0 + (kw >> 1), boh0 + (kh >> 1), bimg);
+                            if (p.pairx) {                                            // pixel-pair view (conv_tc.cuh TcConvDesc::pairx)
+                                const int kh = tap >> 1, j = tap & 1;
+                                tma_load_4d_cg2(sa, &p.tmA[(kh & 1) * 2], fb, cb * BK, bow0 + j, boh0 + (kh >> 1), bimg);
+                            } else {
+                                const int kh = tap / 3, kw = tap - kh * 3;
+                                tma_load_4d_cg2(sa, &p.tmA[(kh & 1) * 2 + (kw & 1)], fb, cb * BK, bow0 + (kw >> 1), boh0 + (kh >> 1), bimg);
+                            }
                         } else {
                             if (p.ksize == 3) { cb = kb / 9; tap = kb - cb * 9; }    // channel block outer, tap inner (as conv_tc.cuh)
                             int shift = 0;
@@ -352,7 +357,10 @@ inline int tc2_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 
 // Plan for the CTA-pair kernel; returns the kernel kind (1 flat, 2 strided box) when the layer is eligible, 0 otherwise.
 inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn, int smem_budget_kb, int group, int nepi, int gw) {
-    if (d.raw_in || d.cin % 64 != 0 || d.split || d.out_f32 || d.upsample) return 0;
+    if (d.pairx && (d.cin != 32 || d.stride != 2 || d.k != 3 || !d.w16_pair || d.in_ld != 32 || d.in_choff != 0)) return 0;
+    const int cin = d.pairx ? 64 : d.cin;
+    const int ntaps = d.pairx ? 6 : d.k * d.k;
+    if (d.raw_in || cin % 64 != 0 || d.split || d.out_f32 || d.upsample) return 0;
     const bool box = d.stride == 2;
     if (box ? (d.k != 3 || nepi != 4 || gw != 32) : (d.stride != 1)) return 0;
     if (d.cout_pad % bn || (nepi != 4 && nepi != 8)) return 0;
@@ -370,9 +378,10 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     if (getenv("Y4_DEBUG_NORES")) p.res = nullptr;                          // timing experiments only (wrong results)
     p.cout_store = d.cout;
     p.ksize = d.k;
-    p.kb_per_tap = d.cin / 64;
-    p.num_kb = d.k * d.k * p.kb_per_tap;
-    const int K = d.k * d.k * d.cin;
+    p.kb_per_tap = cin / 64;
+    p.num_kb = ntaps * p.kb_per_tap;
+    p.pairx = d.pairx;
+    const int K = ntaps * cin;
     const int in_Hp = d.in_H + 2, in_Wp = d.in_H + 2;
     P.in_Hp = in_Hp; P.in_Wp = in_Wp;
     p.Hp = in_Hp; p.Wp = in_Wp;
@@ -382,7 +391,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
         cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)d.cout_pad};
         cuuint64_t str[1] = {(cuuint64_t)K * 2};
         cuuint32_t box2[2] = {64, (cuuint32_t)(bn / 2)};
-        if (!encode_map(&p.tmW, const_cast<__half*>(d.w16), 2, dims, str, box2, 128, err)) return -1;
+        if (!encode_map(&p.tmW, const_cast<__half*>(d.pairx ? d.w16_pair : d.w16), 2, dims, str, box2, 128, err)) return -1;
     }
     if (!box) {
         cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)p.rows_alloc};
@@ -410,7 +419,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
         for (int ph = 0; ph < 2; ph++)
             for (int pw = 0; pw < 2; pw++) {
                 char* b = in_base + ((size_t)ph * in_Wp + pw) * d.in_ld * 2;
-                cuuint64_t dims[4] = {(cuuint64_t)d.cin, (cuuint64_t)in_Wp / 2, (cuuint64_t)in_Hp / 2, (cuuint64_t)d.max_batch};
+                cuuint64_t dims[4] = {(cuuint64_t)cin, (cuuint64_t)in_Wp / 2, (cuuint64_t)in_Hp / 2, (cuuint64_t)d.max_batch};
                 cuuint64_t str[3] = {(cuuint64_t)2 * d.in_ld * 2, (cuuint64_t)2 * in_Wp * d.in_ld * 2, (cuuint64_t)in_Hp * in_Wp * d.in_ld * 2};
                 cuuint32_t box4[4] = {64, (cuuint32_t)bestTW, (cuuint32_t)bestTH, 1};
                 if (!encode_map(&p.tmA[ph * 2 + pw], b, 4, dims, str, box4, 128, err)) return -1;

@@ -68,6 +68,7 @@ struct ConvOp {
     __half* d_w16_lo = nullptr; // split precision: fp16(w*s - fp16(w*s)), s = per-cout power of two
     float* d_wscale = nullptr;  // split precision: 1/s per cout (exact)
     __half* d_w16k32 = nullptr; // conv 0 only: [32][32], K zero-padded 27 -> 32 (conv0_tc.cuh)
+    __half* d_w16_pair = nullptr; // 3x3 stride-2 conv with cin = 32 (conv 1): [cout_pad][6*64] for the pixel-pair view (TcConvDesc::pairx)
     int kind = 0;              // 0 simt, 1 tc flat, 2 tc box
     TcConvPlan tc;             // tensor maps + tile config (conv_tc.cuh)
     TcConvDesc desc{};         // what tc was planned from (the autotuner re-plans candidates from it)
@@ -570,6 +571,16 @@ int upload_weights(y4_engine* e, const unsigned char* data, size_t nbytes) {
         }
         CUDA_TRY(e, cudaMemcpy(c.d_w32, w32.data(), w32.size() * 4, cudaMemcpyHostToDevice));
         CUDA_TRY(e, cudaMemcpy(c.d_w16, w16.data(), w16.size() * 2, cudaMemcpyHostToDevice));
+        if (c.d_w16_pair) {
+            // pixel-pair view: K' = (kh, j, e): j = 0 -> [kw 0 | kw 1], j = 1 -> [kw 2 | zeros], 32 channels each
+            std::vector<__half> wp((size_t)c.cout_pad * 384, __float2half(0.f));
+            for (int o = 0; o < c.cout; o++)
+                for (int kh = 0; kh < 3; kh++)
+                    for (int kw = 0; kw < 3; kw++)
+                        for (int ci = 0; ci < 32; ci++)
+                            wp[(size_t)o * 384 + (kh * 2 + (kw >> 1)) * 64 + (kw & 1) * 32 + ci] = w16[(size_t)o * c.K + (kh * 3 + kw) * 32 + ci];
+            CUDA_TRY(e, cudaMemcpy(c.d_w16_pair, wp.data(), wp.size() * 2, cudaMemcpyHostToDevice));
+        }
         if (c.d_w16k32) {
             std::vector<__half> wk(32 * 32, __float2half(0.f));
             for (int o = 0; o < c.cout && o < 32; o++)
@@ -638,6 +649,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     for (auto& c : e->convs) {
         CREATE_TRY(cudaMalloc(&c.d_w32, sizeof(float) * c.K * c.cout_pad));
         CREATE_TRY(cudaMalloc(&c.d_w16, sizeof(__half) * c.K * c.cout_pad));
+        if (!c.raw_in && c.cin == 32 && c.k == 3 && c.stride == 2) CREATE_TRY(cudaMalloc(&c.d_w16_pair, sizeof(__half) * 384 * c.cout_pad));
         if (c.raw_in && c.K == 27 && c.cout == 32) { CREATE_TRY(cudaMalloc(&c.d_w16k32, sizeof(__half) * 32 * 32)); CREATE_TRY(cudaMemset(c.d_w16k32, 0, sizeof(__half) * 32 * 32)); }
         CREATE_TRY(cudaMalloc(&c.d_bias, sizeof(float) * c.cout_pad));
         if (cfg->precision == Y4_PREC_FP16X3) {
@@ -677,7 +689,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             const Buf& ob = e->bufs[c.out.buf];
             d.out = ob.ptr; d.out_ld = ob.C; d.out_choff = c.out.choff; d.out_f32 = c.out_f32; d.upsample = c.upsample;
             if (c.has_res) { const Buf& rb = e->bufs[c.res.buf]; d.res = rb.ptr; d.res_ld = rb.C; d.res_choff = c.res.choff; }
-            d.w16 = c.d_w16; d.bias = c.d_bias;
+            d.w16 = c.d_w16; d.bias = c.d_bias; d.w16_pair = split ? nullptr : c.d_w16_pair;
             if (split) {
                 d.split = 1; d.w16_lo = c.d_w16_lo; d.wscale = c.d_wscale; d.out_lo = ob.ptr_lo;
                 if (!c.raw_in) d.in_lo = e->bufs[c.in.buf].ptr_lo;
@@ -702,7 +714,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         // barrier x {A-patch reuse, resident weights} x epilogue {per-thread stores, slab + TMA store with 4 or 8 warps}.
         // Every candidate accumulates K in the same order and rounds once, so outputs are bit-identical across them
         // (and therefore across GPUs, whatever each one picks).
-        struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw, cta2, lean; };
+        struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw, cta2, lean, pairx; };
         std::vector<Cand> cands;
         const bool allow_patch = getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '1';    // A-patch plans: correct, never the fastest in context on B200
         const bool allow_bres = !(getenv("Y4_BRES") && getenv("Y4_BRES")[0] == '0');
@@ -710,8 +722,14 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         const int nepi_mode = getenv("Y4_NEPI") ? atoi(getenv("Y4_NEPI")) : 0;  // 4 / 8: only that many epilogue warps
         const int gw_mode = getenv("Y4_GW") ? atoi(getenv("Y4_GW")) : 0;        // 32 / 64: only that slab group width
         if (const char* f = getenv("Y4_FORCE")) {                                 // "bn,kb,patch,group,epi,nepi,bres,gw": that plan wherever it applies
-            Cand cd{}; if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", &cd.bn, &cd.kb, &cd.patch, &cd.group, &cd.epi, &cd.nepi, &cd.bres, &cd.gw, &cd.cta2, &cd.lean) >= 8) cands.push_back(cd);
+            Cand cd{}; if (sscanf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d", &cd.bn, &cd.kb, &cd.patch, &cd.group, &cd.epi, &cd.nepi, &cd.bres, &cd.gw, &cd.cta2, &cd.lean, &cd.pairx) >= 8) cands.push_back(cd);
         } else {
+            for (int g : {1, 2, 3, 6})                                         // conv 1 through the pixel-pair view: single CTA (resident W or not) and CTA pair
+                for (int kb : {112, 224}) {
+                    cands.push_back({64, kb, 0, g, 0, 4, 0, 32, 0, 0, 1});
+                    cands.push_back({64, kb, 0, g, 0, 4, 1, 32, 0, 0, 1});
+                    if (kb == 224) cands.push_back({64, kb, 0, g, 1, 4, 0, 32, 1, 0, 1});
+                }
             static const bool allow_cta2 = !(getenv("Y4_CTA2") && getenv("Y4_CTA2")[0] == '0');
             if (allow_cta2)                                                      // CTA-pair kernel: {N tile, k-blocks per barrier, epilogue warps, group width}
                 for (int bn : {64, 128, 256})
@@ -761,8 +779,11 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                     const Cand& cd = cands[ci];
                     if (!cd.epi && epi_mode == 2 && best[li].p.epi) continue;
                     std::string er2;
-                    if (cd.cta2) { if (tc_plan2(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.group, cd.nepi, cd.gw) != c.kind) continue; }
-                    else if (tc_plan(c.desc, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw, cd.lean) != c.kind) continue;
+                    TcConvDesc dd = c.desc;
+                    dd.pairx = cd.pairx;
+                    if (cd.pairx && !dd.w16_pair) continue;
+                    if (cd.cta2) { if (tc_plan2(dd, &trial[li], &er2, cd.bn, cd.kb, cd.group, cd.nepi, cd.gw) != c.kind) continue; }
+                    else if (tc_plan(dd, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw, cd.lean) != c.kind) continue;
                     has[li] = 1; any = true;
                 }
                 if (!any) continue;
@@ -811,7 +832,7 @@ void y4_destroy(y4_engine* e) {
     for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.first);
     if (e->comm) nccl().CommDestroy(e->comm);
     for (auto& b : e->bufs) { cudaFree(b.ptr); cudaFree(b.ptr_lo); }
-    for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_w16k32); cudaFree(c.d_w16_lo); cudaFree(c.d_wscale); cudaFree(c.d_bias); }
+    for (auto& c : e->convs) { cudaFree(c.d_w32); cudaFree(c.d_w16); cudaFree(c.d_w16k32); cudaFree(c.d_w16_pair); cudaFree(c.d_w16_lo); cudaFree(c.d_wscale); cudaFree(c.d_bias); }
     cudaFree(e->d_img_slot[0]); cudaFree(e->d_img_slot[1]);
     for (int i = 0; i < 2; i++) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); if (e->stage[i]) cudaFreeHost(e->stage[i]); }
     for (int i = 0; i < 2; i++) { cudaFree(e->d_u8[i]); cudaFree(e->d_pre[i]); if (e->h_pre[i]) cudaFreeHost(e->h_pre[i]); }
