@@ -65,20 +65,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append([time.time()] + [c.strip() for c in line.split(',')])
+
+    def window(self, t0, t1):
+        """Keep the samples taken while the GPU was under load ([t0, t1]); all of them if the window caught none."""
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        self.rows = inside or self.rows
 
     def stop(self):
         if not self.proc:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.window(getattr(self, 't0', 0.0), getattr(self, 't1', 1e30))
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
+        rows = [r[1:] for r in self.rows]
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
+        reasons = sorted({names[i] for r in rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': reasons, 'samples': len(sm)}
 
@@ -115,10 +122,31 @@ def run_reference(args, rank):
             'cpu_baseline': {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                              'sample': f'{sample} image per step x {args.steps} steps, numpy+OpenBLAS oracle (tf.keras not installable)'},
             'e2e': {'value': v, 'unit': 'images/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _protect_stdout():
+    """Native libraries (NCCL prints its version banner) write to fd 1; the driver expects ONE JSON line there.  Point fd 1 at
+    stderr for the whole run and keep a private duplicate for the result line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+        sys.stdout = sys.stderr
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -169,12 +197,13 @@ def main():
             eng.allgather_results(B, fetch=False)
 
     # ---- resident timing: value -------------------------------------------------------------------
+    clocks = ClockSampler(local)                       # nvidia-smi takes a few hundred ms to produce its first line: start it early,
+    clocks.start()                                     # keep only the samples taken between the first warm-up step and the last timed launch
     eng.synth_fill(0, rank * B, B)                     # image i depends only on its global index
+    clocks.t0 = time.time()
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    clocks = ClockSampler(local)
-    clocks.start()
     l0 = eng.launch_count()
     eng.timer_begin()
     for _ in range(args.steps):
@@ -202,6 +231,8 @@ def main():
     # per-launch durations (CUDA events on the engine stream around every launch of the forward), grouped by kernel
     # instantiation: the instantiation with the largest share of the step is the one the roofline object describes
     prof = np.median(np.stack([eng.profile_layers(B) for _ in range(5)]), axis=0)
+    eng.sync()
+    clocks.t1 = time.time()
     clk = clocks.stop()
     pk = peaks()
     groups = {}
@@ -323,7 +354,7 @@ def main():
         v, dt = cpu_port_images_per_sec(S, 2, W)
         line['cpu_baseline'] = {'value': v, 'unit': 'images/s', 'cores': cores, 'kind': 'port',
                                 'sample': f'2 images {S}x{S} through the numpy+OpenBLAS oracle ({dt:.1f} s); tf.keras itself is not installable here'}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == '__main__':

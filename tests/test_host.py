@@ -122,3 +122,27 @@ def test_get_detection_data_matches_reference_golden():
     assert [str(t) for t in df.dtypes] == g['dtypes']
     rows = json.loads(df.to_json(orient='values'))
     assert rows == g['rows']
+
+
+def test_bench_flow_with_stub_engine():
+    """bench.py's `ours` arm end to end against a stub engine: exactly ONE line on stdout (native libraries such as NCCL print
+    banners to fd 1; bench.py must keep them off it), valid JSON with every key the contract names."""
+    import json
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, os.path.join(here, 'bench_stub_run.py'), '--steps', '2', '--warmup', '3', '--size', '64', '--batch', '2',
+                        '--no-cpu-baseline'], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline', 'dtype', 'data',
+              'config', 'gpu_launches', 'clocks', 'e2e', 'roofline'):
+        assert k in d, k
+    assert d['steps'] == 2 and d['warmup'] == 3 and d['n_gpus'] == 1 and d['gpu_launches'] == 2 * 116
+    for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic', 'kernel'):
+        assert k in d['roofline'], k
+    for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
+        assert k in d['e2e'], k
+    assert d['e2e']['h2d_bytes_per_step'] == 2 * 64 * 64 * 3
