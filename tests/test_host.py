@@ -146,3 +146,67 @@ def test_bench_flow_with_stub_engine():
     for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
         assert k in d['e2e'], k
     assert d['e2e']['h2d_bytes_per_step'] == 2 * 64 * 64 * 3
+
+
+class _FacadeStubEngine:
+    """Stand-in for binding.Engine: lets the host-side façade logic (batching, formats, flips) run without a GPU."""
+    max_batch = 2
+
+    def __init__(self, **kw):
+        self.calls = []
+        self.queue = []
+
+    def load_darknet(self, path):
+        self.calls.append(('load', path))
+
+    def _out(self, n):
+        boxes = np.zeros((n, 100, 4), np.float32); scores = np.zeros((n, 100), np.float32)
+        classes = np.zeros((n, 100), np.float32); valid = np.full((n,), 2, np.int32)
+        boxes[:, 0] = [0.1, 0.2, 0.5, 0.75]; boxes[:, 1] = [0.0, 0.0, 1.0, 1.0]
+        scores[:, 0] = 0.9; scores[:, 1] = 0.4; classes[:, 1] = 1
+        return [boxes, scores, classes, valid]
+
+    def predict_u8(self, raws, reverse_channels=False, with_indices=False):
+        self.calls.append(('predict_u8', len(raws), reverse_channels))
+        return self._out(len(raws))
+
+    def submit_u8(self, raws, reverse_channels=False):
+        assert len(self.queue) < 2, 'more than two batches in flight'
+        self.calls.append(('submit_u8', len(raws), reverse_channels))
+        self.queue.append(len(raws))
+
+    def collect(self, with_indices=False):
+        return self._out(self.queue.pop(0))
+
+
+def test_facade_host_logic_with_stub_engine(tmp_path, monkeypatch):
+    """predict_img on a raw uint8 image goes through the GPU-preprocess entry point and yields the reference's DataFrame;
+    export_prediction keeps at most two batches in flight, never flips channels (models.py:153) and writes
+    `<class> <score> <x1> <y1> <x2> <y2>` in raw-image pixels (models.py:170-179)."""
+    cv2 = pytest.importorskip('cv2')
+    import y4b200
+    from y4b200 import models
+    monkeypatch.setattr(models, 'Engine', _FacadeStubEngine)
+    names = tmp_path / 'names.txt'
+    names.write_text('person\ncar\n')
+    wfile = tmp_path / 'w.weights'
+    wfile.write_bytes(b'')
+    m = y4b200.Yolov4(weight_path=str(wfile), class_name_path=str(names))
+    assert ('load', str(wfile)) in m.engine.calls
+    raw = np.zeros((200, 400, 3), np.uint8)
+    df = m.predict_img(raw, plot_img=False)
+    assert ('predict_u8', 1, False) in m.engine.calls
+    assert list(df['class_name']) == ['person', 'car'] and list(df['x2']) == [200, 400] and list(df['h']) == [int(0.75 * 200) - int(0.2 * 200), 200]
+    img_dir, pred_dir = tmp_path / 'imgs', tmp_path / 'pred'
+    img_dir.mkdir(); pred_dir.mkdir()
+    for i in range(5):
+        cv2.imwrite(str(img_dir / f'a{i}.png'), np.zeros((100 + i, 50, 3), np.uint8))
+    ann = tmp_path / 'ann.txt'
+    ann.write_text(''.join(f'a{i}.png 1,2,3,4,0\n' for i in range(5)))
+    m.engine.calls.clear()
+    m.export_prediction(str(ann), str(pred_dir), str(img_dir), bs=2)
+    assert [c for c in m.engine.calls if c[0] == 'submit_u8'] == [('submit_u8', 2, False), ('submit_u8', 2, False), ('submit_u8', 1, False)]
+    lines = (pred_dir / 'a3.txt').read_text().splitlines()
+    assert len(lines) == 2
+    cls, score, x1, y1, x2, y2 = lines[0].split(' ')
+    assert cls == 'person' and float(score) == pytest.approx(0.9) and float(x2) == pytest.approx(0.5 * 50) and float(y2) == pytest.approx(0.75 * 103)
