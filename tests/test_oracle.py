@@ -296,3 +296,37 @@ def test_decode_matches_reference_get_boxes_and_flattening(refgraph, weights):
     assert np.abs(boxes[0][flat // 80] - refgraph['a_top_boxes']).max() <= 2e-4
     cnt = int((scores > O.SCORE_THRESHOLD).sum())
     assert abs(cnt - int(refgraph['a_count_above_thr'])) <= 3, (cnt, int(refgraph['a_count_above_thr']))
+
+
+def test_nms_against_torchvision():
+    """Independent library cross-check of the restated combined_non_max_suppression: torchvision.ops.nms (greedy, suppress when
+    IoU > thr, the same rule TF uses) per class on the candidates above the score threshold, then the same top-100 merge.
+    torchvision computes IoU in a different floating-point order, so the crafted heads keep every IoU away from the threshold
+    (margins checked); the selected (box, class) lists must then be identical."""
+    tv = pytest.importorskip('torchvision')
+    import torch
+    S = 160
+    heads = O.synth_heads(seed=11, batch=2, img_size=S, n_clusters=40)
+    boxes, scores = O.decode_heads(heads, S)
+    m = {}
+    ob, osc, ocl, ov, oidx = O.combined_nms(boxes, scores, margins=m)
+    assert m['iou'] > 1e-5 and m['score'] > 1e-6, m
+    for b in range(2):
+        picked = []
+        for c in range(scores.shape[2]):
+            n = np.nonzero(scores[b, :, c] > np.float32(O.SCORE_THRESHOLD))[0]
+            if n.size == 0:
+                continue
+            s = scores[b, n, c]
+            order = np.lexsort((n, -s.astype(np.float64)))          # torchvision visits by score; make ties explicit the same way
+            n, s = n[order], s[order]
+            bb = boxes[b, n]
+            bb = np.stack([np.minimum(bb[:, 0], bb[:, 2]), np.minimum(bb[:, 1], bb[:, 3]), np.maximum(bb[:, 0], bb[:, 2]), np.maximum(bb[:, 1], bb[:, 3])], 1)
+            keep = tv.ops.nms(torch.from_numpy(bb.astype(np.float64)), torch.from_numpy(s.astype(np.float64)), float(np.float32(O.IOU_THRESHOLD))).numpy()
+            keep = np.sort(keep)[:O.MAX_BOXES]                      # indices into the score-ordered list
+            picked += [(float(s[k]), c, int(n[k])) for k in keep]
+        picked.sort(key=lambda t: (-t[0], t[1], t[2]))
+        picked = picked[:O.MAX_BOXES]
+        assert ov[b] == len(picked)
+        assert [p[2] for p in picked] == oidx[b, :ov[b]].tolist()
+        assert [p[1] for p in picked] == ocl[b, :ov[b]].astype(int).tolist()
