@@ -50,9 +50,12 @@ def sigmoid(x):
 # ----------------------------------------------------------------------------------------------
 # conv / pool / upsample  (custom_layers.py:5-31, :130-132, :147)
 # ----------------------------------------------------------------------------------------------
-def conv2d_raw(x, w_hwio, stride):
+def conv2d_raw(x, w_hwio, stride, kperm=None):
     """Cross-correlation, NHWC x HWIO.  stride 1: 'same'.  stride 2: ZeroPadding2D(((1,0),(1,0)))
-    followed by a 'valid' stride-2 conv (custom_layers.py:9-15)."""
+    followed by a 'valid' stride-2 conv (custom_layers.py:9-15).
+    kperm: optional numpy Generator; the K = k*k*Cin terms of every dot product are then summed in a random order
+    (same products, different rounding) -- a second, equally valid floating-point evaluation of the same conv (TF's own
+    summation order is unspecified), used to find test inputs whose detections do not hinge on round-off."""
     B, H, W, Cin = x.shape
     k = w_hwio.shape[0]
     Cout = w_hwio.shape[3]
@@ -73,7 +76,11 @@ def conv2d_raw(x, w_hwio, stride):
             taps = [xp[b, kh:kh + stride * (OH - 1) + 1:stride, kw:kw + stride * (OW - 1) + 1:stride, :]
                     for kh in range(k) for kw in range(k)]
             cols = np.concatenate(taps, axis=-1).reshape(OH * OW, k * k * Cin)
-        out[b] = (cols @ wm).reshape(OH, OW, Cout)
+        if kperm is not None:
+            perm = kperm.permutation(cols.shape[1])
+            out[b] = (np.ascontiguousarray(cols[:, perm]) @ np.ascontiguousarray(wm[perm])).reshape(OH, OW, Cout)
+        else:
+            out[b] = (cols @ wm).reshape(OH, OW, Cout)
     return out
 
 
@@ -222,13 +229,15 @@ def _apply_simple(o, t):
 # ----------------------------------------------------------------------------------------------
 # forward: 110 convs -> 3 raw heads   (models.py:50-52 yolo_model)
 # ----------------------------------------------------------------------------------------------
-def forward(imgs, W: Weights, dtype=np.float32, keep=None, fold_bn=False, quant=None):
+def forward(imgs, W: Weights, dtype=np.float32, keep=None, fold_bn=False, quant=None, kperm_seed=None):
     """imgs (B,S,S,3) in [0,1].  Returns [head_s, head_m, head_l] each (B,g,g,3*(5+nc)).
     keep: optional dict filled with every named intermediate (layer-by-layer parity).
     fold_bn=False follows the reference op order (conv -> BN -> act); fold_bn=True uses folded
     weights (what the engine computes) — used to measure the folding error itself.
-    quant: optional callable applied to every conv output after activation/add (simulates fp16 storage)."""
+    quant: optional callable applied to every conv output after activation/add (simulates fp16 storage).
+    kperm_seed: sum every conv's K terms in a seeded random order (conv2d_raw): another round-off realisation."""
     ops, heads = build_netlist(W.num_classes)
+    kperm = None if kperm_seed is None else np.random.default_rng(kperm_seed)
     t = {'img': np.asarray(imgs).astype(dtype)}          # Keras casts float64 input to float32
     live_until = {}
     for i, o in enumerate(ops):
@@ -240,9 +249,9 @@ def forward(imgs, W: Weights, dtype=np.float32, keep=None, fold_bn=False, quant=
             x = t[o.ins[0]]
             if fold_bn:
                 w, b = W.folded(o.idx, dtype)
-                y = conv2d_raw(x, w, o.stride) + b
+                y = conv2d_raw(x, w, o.stride, kperm) + b
             else:
-                y = conv2d_raw(x, p['w'].astype(dtype), o.stride)
+                y = conv2d_raw(x, p['w'].astype(dtype), o.stride, kperm)
                 if o.bn:   # FusedBatchNorm inference: (x-mean)*gamma/sqrt(var+eps)+beta, in dtype
                     inv = (p['gamma'].astype(dtype) / np.sqrt(p['var'].astype(dtype) + dtype(BN_EPS))).astype(dtype)
                     y = ((y - p['mean'].astype(dtype)) * inv + p['beta'].astype(dtype)).astype(dtype)
@@ -279,7 +288,8 @@ def get_boxes(pred, anchors, num_classes, grid_size, stride, xyscale):
     gx, gy = np.meshgrid(np.arange(grid_size), np.arange(grid_size))   # xy indexing: [...,0]=col, [...,1]=row
     grid = np.stack([gx, gy], axis=-1)[:, :, None, :].astype(f32)       # (g,g,1,2)
     xs, st = f32(xyscale), f32(stride)
-    box_xy = ((box_xy * xs) - f32(0.5) * (xs - f32(1)) + grid) * st     # :251
+    # :251  `0.5 * (xyscale - 1)` is Python float (double) arithmetic in the reference; TF casts the constant to float32
+    box_xy = ((box_xy * xs) - f32(0.5 * (float(xyscale) - 1.0)) + grid) * st
     box_wh = np.exp(box_wh) * anchors.astype(f32)                       # :253
     x1y1 = box_xy - box_wh / f32(2)
     x2y2 = box_xy + box_wh / f32(2)

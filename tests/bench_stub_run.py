@@ -15,7 +15,7 @@ import y4_oracle as O  # noqa: E402
 
 
 class StubEngine:
-    max_boxes = 100
+    max_boxes, num_boxes, num_classes = 100, 22743, 80
 
     def __init__(self, img_size=416, max_batch=1, precision=0, device=0, **kw):
         self.S, self.B, self.n = img_size, max_batch, 0

@@ -59,12 +59,60 @@ def test_runtime_thresholds_and_empty():
     eng.close()
 
 
-def test_capacity_error_is_loud():
+def test_config4_batch32_all_images():
+    """BASELINE config 4 as stated: 608 grids (76/38/19), 80 classes, batch 32, ~1000 candidates per image above 0.3 --
+    every one of the 32 images against the oracle, bit-exact indices."""
     import y4b200
+    import y4_oracle as O
+    S, B = 608, 32
+    heads = O.synth_heads(seed=4, batch=B, img_size=S, n_clusters=150)
+    m = {}
+    ref = O.decode_nms(heads, S, margins=m)
+    assert m['score'] > 1e-6 and m['iou'] > 1e-5, m
+    eng = y4b200.Engine(img_size=S, max_batch=B)
+    got = eng.decode_nms(heads, with_indices=True)
+    _check(got, ref, 'decode_nms_608_b32')
+    eng.close()
+
+
+def test_no_candidate_limit():
+    """tf.image.combined_non_max_suppression has no cap on candidates (custom_layers.py:290-297).  The fast path keeps
+    8192 keys per image; images beyond that go through nms_overflow_kernel and must still equal the oracle: (a) 14,000
+    distinct candidates in one image next to a normal image, (b) every (box, class) of an image hot (504,000 candidates,
+    all scores tied: the documented tie order box-index-ascending decides), (c) a very low runtime score threshold."""
+    import y4b200
+    import y4_oracle as O
     S = 320
-    eng = y4b200.Engine(img_size=S, max_batch=1)
+    eng = y4b200.Engine(img_size=S, max_batch=2)
+    many = O.synth_heads(seed=9, batch=1, img_size=S, n_clusters=2000)
+    few = O.synth_heads(seed=10, batch=1, img_size=S, n_clusters=30)
+    heads = [np.concatenate([a, b], axis=0) for a, b in zip(many, few)]
+    boxes, scores = O.decode_heads(heads, S)
+    ncand = (scores > np.float32(0.3)).sum(axis=(1, 2))
+    assert ncand[0] > 8192 > ncand[1] > 0, ncand
+    _check(eng.decode_nms(heads, with_indices=True), O.combined_nms(boxes, scores), 'overflow_14k')
     hot = [np.full((1, S // s, S // s, 255), 10.0, np.float32) for s in (8, 16, 32)]   # every (box,class) passes
-    with pytest.raises(y4b200.Y4Error) as ei:
-        eng.decode_nms(hot)
-    assert ei.value.code == -5
+    _check(eng.decode_nms(hot, with_indices=True), O.decode_nms(hot, S), 'overflow_all_hot')
+    _check(eng.decode_nms(few, 0.413, 1e-4, with_indices=True), O.decode_nms(few, S, score_threshold=1e-4), 'overflow_low_thr')
+    eng.close()
+
+
+def test_long_class_segment():
+    """More than 1024 candidates of ONE class in an image that still fits the fast path (arg-max rounds instead of the
+    shared-memory rank sort in nms_class_kernel)."""
+    import y4b200
+    import y4_oracle as O
+    S = 416
+    heads = O.synth_heads(seed=12, batch=1, img_size=S, n_clusters=20)
+    rng = np.random.default_rng(0)
+    h = heads[0].reshape(1, S // 8, S // 8, 3, 85)
+    pick = rng.choice(h.shape[1] * h.shape[2] * 3, 3000, replace=False)
+    r, c, a = np.unravel_index(pick, (h.shape[1], h.shape[2], 3))
+    h[0, r, c, a, 4] = rng.uniform(1, 6, 3000).astype(np.float32)
+    h[0, r, c, a, 5 + 7] = rng.uniform(1, 6, 3000).astype(np.float32)
+    boxes, scores = O.decode_heads(heads, S)
+    per_class = (scores[0] > np.float32(0.3)).sum(axis=0)
+    assert per_class[7] > 1024 and per_class.sum() <= 8192, (per_class[7], per_class.sum())
+    eng = y4b200.Engine(img_size=S, max_batch=1)
+    _check(eng.decode_nms(heads, with_indices=True), O.combined_nms(boxes, scores), 'long_segment')
     eng.close()

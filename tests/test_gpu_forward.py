@@ -43,30 +43,51 @@ def test_fp32_layer_by_layer(weights, size, batch):
         assert _rel(a, b) < 1e-4
 
 
-def _stable_case(W, size, tries=8):
-    """Find a seeded image whose detections do not depend on fp32 round-off: fp32 and fp64 evaluations of the
-    oracle pick the same boxes in the same order (SURVEY §7 'hard parts': ties / near-threshold cases are
-    implementation-defined in TF too)."""
+_STABLE_CACHE = {}
+
+
+def _stable_case(W, size, tries=12, start=0):
+    """Find a seeded image whose detections do not hinge on fp32 round-off.  TF's summation order is unspecified and the
+    outputs hold ~100 scores whose closest pair is typically 1e-5 apart, so for most images two equally valid fp32
+    evaluations of the reference already disagree on the ORDER of two detections (SURVEY §7 'hard parts': ties and
+    near-threshold cases are implementation-defined in TF too).  'Bit-exact indices' is therefore tested on images where
+    four evaluations of the oracle agree on every index -- fp32, fp64, and fp32 with the K terms of every dot product
+    summed in two other (seeded random) orders -- i.e. on images that are round-off stable for ANY correct fp32
+    implementation, not for ours in particular.  `noise` = the largest score / coordinate difference among them."""
     import y4_oracle as O
-    for first in range(tries):
+    if (size, start) in _STABLE_CACHE:
+        return _STABLE_CACHE[(size, start)]
+    for first in range(start, start + tries):
         imgs = O.synth_images(0, first, 1, size)
-        h32 = O.forward(imgs, W)
-        h64 = [h.astype(np.float32) for h in O.forward(imgs, W, np.float64)]
-        r32, r64 = O.decode_nms(h32, size), O.decode_nms(h64, size)
-        if np.array_equal(r32[4], r64[4]) and r32[3][0] > 0:
-            noise = max(float(np.abs(r32[0] - r64[0]).max()), float(np.abs(r32[1] - r64[1]).max()))
+        r32 = O.decode_nms(O.forward(imgs, W), size)
+        if r32[3][0] == 0:
+            continue
+        noise, ok = 0.0, True
+        for kw in (dict(dtype=np.float64), dict(kperm_seed=1), dict(kperm_seed=2)):
+            r = O.decode_nms([h.astype(np.float32) for h in O.forward(imgs, W, **kw)], size)
+            if not np.array_equal(r[4], r32[4]):
+                ok = False
+                break
+            noise = max(noise, float(np.abs(r[0] - r32[0]).max()), float(np.abs(r[1] - r32[1]).max()))
+        if ok:
+            _STABLE_CACHE[(size, start)] = (imgs, r32, noise, first)
             return imgs, r32, noise, first
     raise AssertionError('no round-off-stable synthetic image found')
 
 
-@pytest.mark.parametrize('size', [256, 416])
-def test_fp32_predict_end_to_end(weights, size):
-    """inference_model.predict parity (BASELINE config 1 at 416): bit-exact indices / classes / valid; boxes and
-    scores within 1e-4 (north_star tolerance), widened only if fp32 round-off of the oracle itself exceeds it."""
+# first image index to try per size (found with the same _stable_case search; the test re-verifies the stability)
+STABLE_START = {256: 3, 416: 0, 608: 4}
+
+
+@pytest.mark.parametrize('size', [256, 416, 608])
+def test_fp32_predict_end_to_end_on_roundoff_stable_image(weights, size):
+    """inference_model.predict parity (BASELINE config 1 at 416, the bench resolution 608): bit-exact indices / classes /
+    valid on a round-off-stable image (_stable_case); boxes and scores within 1e-4 (north_star tolerance), widened only
+    if fp32 round-off of the oracle itself exceeds it."""
     import y4b200
     import y4_oracle as O
     W, blob = weights
-    imgs, ref, noise, first = _stable_case(W, size)
+    imgs, ref, noise, first = _stable_case(W, size, start=STABLE_START[size])
     tol = max(1e-4, 3 * noise)
     eng = y4b200.Engine(img_size=size, max_batch=1, precision=y4b200.PREC_FP32)
     eng.load_darknet_bytes(blob)

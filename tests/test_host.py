@@ -141,8 +141,11 @@ def test_bench_flow_with_stub_engine():
               'config', 'gpu_launches', 'clocks', 'e2e', 'roofline'):
         assert k in d, k
     assert d['steps'] == 2 and d['warmup'] == 3 and d['n_gpus'] == 1 and d['gpu_launches'] == 2 * 116
-    for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic', 'kernel'):
+    for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic', 'kernel', 'frac_of_burst_peak', 'frac_of_sustained_peak'):
         assert k in d['roofline'], k
+    for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'us_per_img'):
+        assert k in d['decode_nms'], k
+    assert set(d['parity_modes']) >= {'fp16x3', 'fp32'}
     for k in ('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'):
         assert k in d['e2e'], k
     assert d['e2e']['h2d_bytes_per_step'] == 2 * 64 * 64 * 3

@@ -1,10 +1,14 @@
 """CPU tests (-m "not gpu"): the oracle against independent implementations and the reference's structural
 known-answers (the reference has no tests and no replayable golden vector -> parity unpinned)."""
+import os
+
 import numpy as np
 import pytest
 
 import netspec
 import y4_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_netlist_known_answers():
@@ -330,3 +334,39 @@ def test_nms_against_torchvision():
         assert ov[b] == len(picked)
         assert [p[2] for p in picked] == oidx[b, :ov[b]].tolist()
         assert [p[1] for p in picked] == ocl[b, :ov[b]].astype(int).tolist()
+
+
+def test_c_nms_restatement_equals_python_oracle():
+    """oracle/nms_ref.c (compiled CPU baseline of combined_non_max_suppression) == y4_oracle.combined_nms, bit for bit,
+    including runtime thresholds, ties (all-equal scores), the empty case and the top-100 cut."""
+    import subprocess
+    src, lib = os.path.join(ROOT, 'oracle', 'nms_ref.c'), os.path.join(ROOT, 'oracle', 'libnmsref.so')
+    if not os.path.exists(lib) or os.path.getmtime(lib) < os.path.getmtime(src):
+        subprocess.run(['gcc', '-O2', '-fPIC', '-shared', '-ffp-contract=off', '-fopenmp', src, '-o', lib, '-lm'], check=True)
+    import y4_cpu_fast as F
+    for seed, S, clusters, iou, thr in ((3, 320, 150, 0.413, 0.3), (4, 160, 40, 0.6, 0.1), (5, 160, 400, 0.2, 0.5)):
+        heads = O.synth_heads(seed=seed, batch=2, img_size=S, n_clusters=clusters)
+        boxes, scores = O.decode_heads(heads, S)
+        ref = O.combined_nms(boxes, scores, iou, thr)
+        got = F.combined_nms_c(boxes, scores, iou, thr)
+        for a, b in zip(ref, got):
+            assert np.array_equal(a, b)
+    hot = [np.full((1, 64 // s, 64 // s, 255), 10.0, np.float32) for s in (8, 16, 32)]
+    cold = [np.full_like(h, -20.0) for h in hot]
+    for heads in (hot, cold):
+        boxes, scores = O.decode_heads(heads, 64)
+        for a, b in zip(O.combined_nms(boxes, scores), F.combined_nms_c(boxes, scores)):
+            assert np.array_equal(a, b)
+
+
+def test_torch_cpu_forward_matches_numpy_oracle():
+    """oracle/y4_cpu_fast.TorchNet (oneDNN convs; bench.py's CPU baseline) follows the same netlist and op order as the
+    numpy oracle: heads agree to fp32 round-off of a 110-layer evaluation."""
+    import y4_cpu_fast as F
+    W = O.synth_weights(seed=1)
+    imgs = O.synth_images(0, 0, 2, 96)
+    want = O.forward(imgs, W)
+    got = F.TorchNet(W).forward(imgs)
+    for a, b in zip(got, want):
+        assert a.shape == b.shape
+        assert float(np.abs(a - b).max() / np.abs(b).max()) < 3e-4

@@ -237,7 +237,7 @@ class Engine:
         if not inflight:                      # nothing submitted: let the engine report it (Y4_ERR_ARG -> Y4Error)
             boxes, scores, classes, valid, idx = self._alloc_out(1)
             self._chk(self._lib.y4_collect(self._h, 1, _ptr(boxes), _ptr(scores), _ptr(classes), _ptr(valid), _ptr(idx)))
-            raise Y4Error('collect() without a matching submit()')
+            raise Y4Error(-4, 'collect() without a matching submit()')
         imgs = inflight.pop(0)
         b = imgs.shape[0]
         boxes, scores, classes, valid, idx = self._alloc_out(b)

@@ -27,6 +27,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
+#include <cmath>
 #include <string>
 
 namespace y4 {
@@ -57,6 +59,10 @@ struct TcParams {
     const __half* res;
     const __half* res_lo;
     int split;
+    int chunk_kb;                // split precision: k-blocks accumulated inside the tensor core per TMEM partial (1 = every k-block is
+                                 // drained and summed round-to-nearest by the epilogue warps; >= num_kb = the old whole-K accumulation)
+    float chunk_comp;            // split precision: every drained partial is multiplied by this (1 + eps) in the fused add -- the mean of
+                                 // the tensor core's round-toward-zero loss over the hi*hi MMAs of one chunk (1.0 = no compensation)
     float act_scale, inv_act_scale;   // split precision: stored activations = true value * 2^8 (keeps the lo plane out of fp16 subnormals)
     int out_ld, out_choff, res_ld, res_choff;
     int act, out_f32, upsample;
@@ -500,7 +506,8 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // as many epilogue warps per SM as two 8-warp CTAs, but four independent tile pipelines.
 template <int BN, int BK, bool SPLIT, int NEPI, bool LEAN = false>
 __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) conv_tc_kernel(const __grid_constant__ TcParams p) {
-    static_assert(NEPI == 4 || (NEPI == 8 && !SPLIT), "8 epilogue warps: slab epilogue only");
+    static_assert(NEPI == 4 || NEPI == 8, "4 or 8 epilogue warps");
+    static_assert(!SPLIT || BN / (NEPI / 4) <= 64, "split precision: each epilogue warp sums at most 64 accumulator columns in registers");
     static_assert(!LEAN || (NEPI == 4 && !SPLIT && BN == 64), "lean 4-CTA/SM variant: 64-wide tiles, slab epilogue only");
     constexpr int SWZ = BK * 2;
     constexpr int A_BYTES = 128 * BK * 2;
@@ -699,6 +706,48 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
             long long w_full = 0, w_tempty = 0, w_pfull = 0;
             const long long t_mma0 = clock64();
             if (p.bres) { mbar_wait(bar_w, 0u); tc_fence_after(); }
+            if constexpr (SPLIT) {
+                // Split precision, CHUNKED accumulation.  The tensor core's fp32 accumulate truncates (round toward zero): every
+                // MMA that adds into a non-zero accumulator loses up to one ulp of it, always in the same direction, and over the
+                // K/16 x 3 MMAs of a layer that bias reaches 1e-5 of the output.  So the tensor core only ever accumulates
+                // `chunk_kb` k-blocks (default one: 64 channels of one tap) into a fresh TMEM partial -- the small cross terms
+                // first, then the four hi*hi MMAs -- and the epilogue warps sum the partials round-to-nearest in registers.
+                // The two TMEM accumulator stages alternate per CHUNK (tfull / tempty count chunks, not tiles).
+                uint32_t ci = 0;
+                const int CH = p.chunk_kb < 1 ? 1 : p.chunk_kb;
+                for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
+                    for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
+                        const uint32_t s = it % (uint32_t)S;
+                        const uint32_t ph = (it / (uint32_t)S) & 1u;
+                        mbar_wait_t(bar_full + 8u * s, ph, dbg ? &w_full : nullptr);
+                        tc_fence_after();
+                        if (it == 0) Y4_STAMP(4);
+                        const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
+                        for (int kk = 0; kk < gcount; kk++) {
+                            const int kb = kb0 + kk;
+                            const int cpos = kb % CH;                                   // position inside the chunk
+                            const uint32_t as = ci & 1u, aph = (ci >> 1) & 1u;
+                            if (cpos == 0) { mbar_wait_t(bar_tempty + 8u * as, aph ^ 1u, dbg ? &w_tempty : nullptr); tc_fence_after(); }
+                            const uint32_t tacc = tmem_base + as * (uint32_t)BN;
+                            const uint32_t sa = ring0 + (s * (uint32_t)G + (uint32_t)kk) * ASTRIDE;
+                            const uint64_t da = make_smem_desc<SWZ>(sa);
+                            const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
+                            const uint64_t la = make_smem_desc<SWZ>(sa + STAGE_BYTES);
+                            const uint64_t lb = make_smem_desc<SWZ>(sa + STAGE_BYTES + A_BYTES);
+                            // (a_hi + a_lo)(b_hi + b_lo) without the a_lo*b_lo term (2^-22 relative)
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) umma_f16(tacc, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (cpos | k) ? 1u : 0u);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) umma_f16(tacc, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), IDESC, 1u);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++) umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, 1u);
+                            if (cpos == CH - 1 || kb == p.num_kb - 1) { umma_commit(bar_tfull + 8u * as); ci++; }   // partial complete
+                        }
+                        umma_commit(bar_empty + 8u * s);
+                    }
+                    if (ti == 0) Y4_STAMP(5);
+                }
+            } else
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
                 const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
                 mbar_wait_t(bar_tempty + 8u * as, aph ^ 1u, dbg ? &w_tempty : nullptr);   // epilogue has drained this accumulator stage
@@ -748,21 +797,9 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                         const uint32_t sa = ring0 + (s * (uint32_t)G + (uint32_t)kk) * ASTRIDE;
                         const uint64_t da = make_smem_desc<SWZ>(sa);
                         const uint64_t db = make_smem_desc<SWZ>(p.bres ? base + (uint32_t)(kb0 + kk) * (uint32_t)B_BYTES : sa + A_BYTES);
-                        if (SPLIT) {
-                            // (a_hi + a_lo)(b_hi + b_lo) without the a_lo*b_lo term (2^-22 relative): small terms first
-                            const uint64_t la = make_smem_desc<SWZ>(sa + STAGE_BYTES);
-                            const uint64_t lb = make_smem_desc<SWZ>(sa + STAGE_BYTES + A_BYTES);
-#pragma unroll
-                            for (int k = 0; k < BK / 16; k++) {
-                                umma_f16(tacc, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
-                                umma_f16(tacc, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), IDESC, 1u);
-                                umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, 1u);
-                            }
-                        } else {
 #pragma unroll
                         for (int k = 0; k < BK / 16; k++)
                             umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
-                        }
                     }
                     umma_commit(bar_empty + 8u * s);        // frees this smem stage once the MMAs have read it
                 }
@@ -779,6 +816,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
         constexpr int NCH = BN / 32;                        // 32-column groups per tile
         const int r = q * 32 + lane;                        // row of the tile
         uint32_t ti = 0, sit = 0;                           // sit: slab groups issued by this warp (epi = 1)
+        [[maybe_unused]] uint32_t ci = 0;                   // split precision: TMEM partials consumed so far (see the MMA warp)
         const bool slab_epi = !SPLIT && p.epi;
         const bool has_res = p.res != nullptr;
         const bool gw64 = p.epi_gw == 64 && !p.out_f32;     // 64-channel groups: NEPI == 4 only (host)
@@ -809,6 +847,55 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                 const int oh = tc.oh0 + th, ow = tc.ow0 + tw;
                 valid = (r < p.TH * p.TW) && oh < p.OH && ow < p.OW;
                 drow = ((long long)tc.img * (p.OH + 2) + oh + 1) * (p.OW + 2) + ow + 1;
+            }
+            if constexpr (SPLIT) {
+                // sum the per-chunk TMEM partials round-to-nearest in registers (this warp: COLS columns of its 32 rows), then
+                // the usual per-thread epilogue on the sums
+                constexpr int COLS = BN / NSETS, NG = COLS / 32;
+                uint32_t acc[NG][32];
+                const int CH = p.chunk_kb < 1 ? 1 : p.chunk_kb;
+                const int nchunks = (p.num_kb + CH - 1) / CH;
+#pragma unroll 1
+                for (int ch = 0; ch < nchunks; ch++, ci++) {
+                    const uint32_t cs = ci & 1u, cph = (ci >> 1) & 1u;
+                    mbar_wait(bar_tfull + 8u * cs, cph);
+                    tc_fence_after();
+                    if (ti == 0 && ch == 0 && threadIdx.x == 64) Y4_STAMP(6);
+                    const uint32_t tpart = tmem_base + ((uint32_t)(q * 32) << 16) + cs * (uint32_t)BN + (uint32_t)(set * COLS);
+                    if (ch == 0) {
+#pragma unroll
+                        for (int g = 0; g < NG; g++) tmem_ld32_issue(tpart + (uint32_t)(32 * g), acc[g]);
+#pragma unroll
+                        for (int g = 0; g < NG; g++) tmem_ld_wait(acc[g]);
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8u * cs);
+#pragma unroll
+                        for (int g = 0; g < NG; g++)
+#pragma unroll
+                            for (int j = 0; j < 32; j++) acc[g][j] = __float_as_uint(__fmul_rn(__uint_as_float(acc[g][j]), p.chunk_comp));
+                    } else {
+                        uint32_t v[NG][32];
+#pragma unroll
+                        for (int g = 0; g < NG; g++) tmem_ld32_issue(tpart + (uint32_t)(32 * g), v[g]);
+#pragma unroll
+                        for (int g = 0; g < NG; g++) tmem_ld_wait(v[g]);
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8u * cs);
+#pragma unroll
+                        for (int g = 0; g < NG; g++)
+#pragma unroll
+                            for (int j = 0; j < 32; j++) acc[g][j] = __float_as_uint(__fmaf_rn(__uint_as_float(v[g][j]), p.chunk_comp, __uint_as_float(acc[g][j])));
+                    }
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const int col0 = tc.n0 + set * COLS + 32 * g;
+                    if (valid && col0 < p.cout_store) epilogue_chunk<true>(p, acc[g], sbias, sscale, col0, drow, n, hp, wp);
+                }
+                __syncwarp();
+                if (ti == 0 && threadIdx.x == 64) Y4_STAMP(7);
+                continue;
             }
             mbar_wait(bar_tfull + 8u * as, aph);
             tc_fence_after();
@@ -934,6 +1021,20 @@ inline bool encode_map(CUtensorMap* m, void* base, int rank, const cuuint64_t* d
     return true;
 }
 
+// "Has this been done on the current device yet?" for per-device, per-function settings such as
+// cudaFuncAttributeMaxDynamicSharedMemorySize: one bit per device ordinal.  Engines on different GPUs may live in one
+// process and run on different threads; setting an attribute twice is harmless, never setting it makes launches fail.
+struct DeviceOnce {
+    std::atomic<unsigned long long> mask{0ull};
+    int dev_ = 0;
+    bool first_use() {
+        cudaGetDevice(&dev_);
+        const unsigned long long bit = 1ull << (dev_ & 63);
+        return !(mask.fetch_or(bit, std::memory_order_acq_rel) & bit);
+    }
+    void forget() { mask.fetch_and(~(1ull << (dev_ & 63)), std::memory_order_acq_rel); }
+};
+
 inline bool pdl_enabled() {
     static const bool on = !(getenv("Y4_PDL") && getenv("Y4_PDL")[0] == '0');
     return on;
@@ -941,11 +1042,10 @@ inline bool pdl_enabled() {
 
 template <int BN, int BK, bool SPLIT, int NEPI, bool LEAN = false>
 inline cudaError_t launch_inst2(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;                                    // per instantiation; the attribute is per device
+    if (once.first_use()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BN, BK, SPLIT, NEPI, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
-        if (e != cudaSuccess) return e;
-        configured = true;
+        if (e != cudaSuccess) { once.forget(); return e; }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(64 + 32 * NEPI); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;
@@ -957,14 +1057,20 @@ inline cudaError_t launch_inst2(const TcConvPlan& pl, dim3 grid, cudaStream_t st
 }
 template <int BN, int BK>
 inline cudaError_t launch_inst(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
-    if (pl.p.split) return launch_inst2<BN, BK, true, 4>(pl, grid, st);
+    if (pl.p.split) {                                          // split precision: <= 64 accumulator columns per epilogue warp
+        if constexpr (BN == 64) return launch_inst2<BN, BK, true, 4>(pl, grid, st);
+        else if constexpr (BN == 128) return launch_inst2<BN, BK, true, 8>(pl, grid, st);
+        else return cudaErrorInvalidValue;
+    }
     if constexpr (BN == 64) { if (pl.lean) return launch_inst2<BN, BK, false, 4, true>(pl, grid, st); }
     return pl.nepi == 8 ? launch_inst2<BN, BK, false, 8>(pl, grid, st) : launch_inst2<BN, BK, false, 4>(pl, grid, st);
 }
 
-inline int sm_count() {
-    static int n = 0;
-    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+inline int sm_count() {                                        // of the CURRENT device (engines on several GPUs may share the process)
+    static std::atomic<int> cache[64];
+    int dev = 0; cudaGetDevice(&dev);
+    int n = cache[dev & 63].load(std::memory_order_relaxed);
+    if (!n) { cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; cache[dev & 63].store(n, std::memory_order_relaxed); }
     return n;
 }
 
@@ -1018,7 +1124,24 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     p.bias = d.bias; p.out = d.out; p.res = reinterpret_cast<const __half*>(d.res);
     p.act_scale = d.split ? 256.f : 1.f; p.inv_act_scale = d.split ? 1.f / 256.f : 1.f;
     p.split = d.split; p.out_lo = d.out_lo; p.res_lo = reinterpret_cast<const __half*>(d.res_lo); p.wscale = d.wscale;
-    if (d.split && (patch || bk != 64 && bk != 32)) return 0;
+    if (d.split && (patch || (bk != 64 && bk != 32) || bn > 128 || epi || bres || lean)) return 0;
+    if (d.split) nepi = bn == 128 ? 8 : 4;                     // launch_inst: <= 64 accumulator columns per epilogue warp
+    p.chunk_kb = 1;
+    if (const char* env = getenv("Y4_SPLIT_CHUNK")) { const int v = atoi(env); if (v >= 1) p.chunk_kb = v; }   // experiments: 1 (default) .. whole K
+    {
+        // Mean of the tensor core's round-toward-zero loss, given back in the epilogue's fused add (acc += partial * (1 + eps)).
+        // Model: the n = BK/16 hi*hi MMAs of a chunk each lose 0.5 ulp of the running sum on average (measured on B200: 0.42 ulp per
+        // MMA, whole-K accumulation, tools/exp_split.py), the running sum grows ~ sqrt(j/n), and the mean relative ulp of a float
+        // is 0.72 * 2^-23:  eps = 0.72 * 2^-23 * sum_j 0.5 sqrt(j/n) = 1.11 * 2^-23 for BK = 64.  1 + eps is rounded to float,
+        // i.e. to 1 + 2^-23.  Measured effect at conv 108 (vs the float64 evaluation): 1.0e-4 -> 4.8e-5, where the fp32 oracle
+        // itself is at 5.9e-5 (profiles/r02_split_chunk.md).  Y4_SPLIT_COMP scales eps (0 disables); whole-K chunks get none.
+        const int n = bk / 16;
+        double f = 0.0;
+        for (int j = 1; j <= n; j++) f += 0.5 * std::sqrt((double)j / n);
+        double m = 1.0;
+        if (const char* env = getenv("Y4_SPLIT_COMP")) m = atof(env);
+        p.chunk_comp = p.chunk_kb == 1 ? (float)(1.0 + m * f * 0.72 * std::ldexp(1.0, -23)) : 1.0f;
+    }
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
     p.act = d.act; p.out_f32 = d.out_f32; p.upsample = d.upsample;
     if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);
@@ -1080,7 +1203,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
             }
     }
     size_t epi_bytes = 0;
-    if (nepi != 4 && (nepi != 8 || !epi)) return 0;
+    if (nepi != 4 && (nepi != 8 || !(epi || d.split))) return 0;
     if (lean && (!epi || nepi != 4 || bn != 64 || d.split)) return 0;
     P.nepi = nepi; P.lean = lean;
     if (epi) {

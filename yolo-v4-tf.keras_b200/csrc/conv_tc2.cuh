@@ -305,11 +305,10 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
 
 template <int BN, int NEPI>
 inline cudaError_t launch_tc2(const TcConvPlan& pl, dim3 grid, cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce once;
+    if (once.first_use()) {
         cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN, NEPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
-        if (e != cudaSuccess) return e;
-        configured = true;
+        if (e != cudaSuccess) { once.forget(); return e; }
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = dim3(64 + 32 * NEPI); cfg.dynamicSmemBytes = pl.smem; cfg.stream = st;

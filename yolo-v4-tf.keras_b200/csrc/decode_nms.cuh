@@ -8,7 +8,8 @@
 
 namespace y4 {
 
-constexpr int kCandCap = 8192;     // Y4_MAX_CANDIDATES
+constexpr int kCandCap = 8192;     // Y4_MAX_CANDIDATES: candidate-list capacity per image of the FAST path; images with more
+                                   // candidates are handled exactly by nms_overflow_kernel (no limit, as in TF)
 constexpr int kSelCap = 8192;      // >= num_classes * max_boxes
 constexpr int kMaxBoxesCap = 128;  // max_boxes upper bound (per-warp selected list in smem)
 
@@ -46,6 +47,20 @@ __device__ __forceinline__ unsigned long long merge_key(int cls, float score, in
     return ((unsigned long long)(~__float_as_uint(score)) << 32) | ((unsigned long long)cls << 24) | (unsigned long long)box;
 }
 
+// The 5 + nc logits of flat box n = off_scale + (row*g + col)*3 + a of image img (custom_layers.py:232-237, 274-280).
+__device__ __forceinline__ const float* box_logits(const DecodeParams& p, int img, int n, int& s, int& a, int& row, int& col) {
+    s = n < p.box_off[1] ? 0 : (n < p.box_off[2] ? 1 : 2);
+    const int ln = n - p.box_off[s];
+    const int lc = ln / 3;
+    a = ln - lc * 3;
+    const int g = p.g[s];
+    row = lc / g; col = lc - row * g;
+    const float* cellp = p.padded[s]
+        ? p.head[s] + (((long long)img * (g + 2) + row + 1) * (g + 2) + col + 1) * p.ld[s]
+        : p.head[s] + (((long long)img * g + row) * g + col) * p.ld[s];
+    return cellp + a * p.C;
+}
+
 // One thread per box (cell, anchor): objectness test first (score = obj * cls <= obj since cls <= 1 and the product is
 // rounded to nearest, so a box whose objectness fails can produce no candidate).  The few boxes that pass are then expanded
 // by the whole warp, one after the other: lanes take the classes, candidates are appended with one atomic per ballot, and
@@ -55,22 +70,14 @@ __global__ void __launch_bounds__(256) decode_filter_kernel(DecodeParams p) {
     const int lane = threadIdx.x & 31;
     const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)p.batch * p.N;
-    int img = 0, n = 0, s = 0, lc = 0, a = 0, row = 0, col = 0;
+    int img = 0, n = 0, s = 0, a = 0, row = 0, col = 0;
     const float* q = nullptr;
     float obj = 0.f;
     bool pass = false;
     if (gt < total) {
         img = (int)(gt / p.N);
         n = (int)(gt - (long long)img * p.N);
-        s = n < p.box_off[1] ? 0 : (n < p.box_off[2] ? 1 : 2);
-        const int ln = n - p.box_off[s];
-        lc = ln / 3; a = ln - lc * 3;
-        const int g = p.g[s];
-        row = lc / g; col = lc - row * g;
-        const float* cellp = p.padded[s]
-            ? p.head[s] + (((long long)img * (g + 2) + row + 1) * (g + 2) + col + 1) * p.ld[s]
-            : p.head[s] + (((long long)img * g + row) * g + col) * p.ld[s];
-        q = cellp + a * p.C;
+        q = box_logits(p, img, n, s, a, row, col);
         obj = sigmoid_rn(q[4]);
         pass = obj > p.score_thr;
     }
@@ -148,25 +155,41 @@ struct NmsParams {
     float* out_classes;    // [batch][max_boxes]
     int* out_valid;        // [batch]
     int* out_idx;          // [batch][max_boxes]
-    int* overflow;         // set to 1 if any image exceeded kCandCap
 };
 
 // combined_non_max_suppression as three small kernels whose parallelism is (image, class), not image:
 //   nms_bucket_kernel  one CTA per image: counting sort of the candidate keys by class (smem histogram + scatter)
 //   nms_class_kernel   one CTA per (image, class): rank sort of the segment (score desc, box asc; keys are unique),
 //                      then warp 0 runs TF's greedy scan (iou > thr strict, against already selected boxes)
-//   nms_merge_kernel   one CTA per image: every survivor finds its global rank (score desc, class asc, box asc) by a
-//                      binary search in each class list; ranks < max_boxes are the output, clipped to [0,1]
+//                      (segments longer than kClassSmemKeys: greedy by repeated block-wide arg-max, no sort)
+//   nms_overflow_kernel one CTA per (image, class), only for images whose candidates did not fit kCandCap: the same greedy
+//                      selection by repeated arg-max straight from the head tensors -- exact for ANY number of candidates
+//   nms_merge_kernel   one CTA per image: k-way merge of the per-class survivor lists, first max_boxes, clipped to [0,1]
 constexpr int kBucketThreads = 1024;
 constexpr int kClassThreads = 128;
 constexpr int kClassSmemKeys = 1024;
 constexpr int kMergeThreads = 256;                            // >= num_classes (255 max): one thread per class list
 
+// block-wide minimum of a 64-bit key, result in every thread (T threads, all participate; contains two barriers)
+template <int T>
+__device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v) {
+    __shared__ unsigned long long wmin_[T / 32];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, d); v = o < v ? o : v; }
+    __syncthreads();                                        // previous round's readers are done with wmin_
+    if ((threadIdx.x & 31) == 0) wmin_[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long best = wmin_[0];
+#pragma unroll
+    for (int w = 1; w < T / 32; w++) best = wmin_[w] < best ? wmin_[w] : best;
+    return best;
+}
+
 __global__ void __launch_bounds__(kBucketThreads) nms_bucket_kernel(NmsParams p) {
     __shared__ int hist[256], cursor[256];
     const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     int cnt = p.cand_count[img];
-    if (cnt > kCandCap) { if (tid == 0) *p.overflow = 1; cnt = kCandCap; }
+    if (cnt > kCandCap) cnt = kCandCap;                     // this image is redone exactly by nms_overflow_kernel
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
     constexpr int PER = kCandCap / kBucketThreads;
@@ -202,10 +225,51 @@ __global__ void __launch_bounds__(kClassThreads) nms_class_kernel(NmsParams p) {
     __shared__ float4 selbox[kMaxBoxesCap];
     const int img = blockIdx.x / p.nc, c = blockIdx.x - img * p.nc;
     const int tid = threadIdx.x, lane = tid & 31;
+    if (p.cand_count[img] > kCandCap) return;              // truncated candidate list: nms_overflow_kernel owns this image
     const int lo = p.seg_start[img * 257 + c], L = p.seg_start[img * 257 + c + 1] - lo;
     if (L == 0) { if (tid == 0) p.nwin[img * 256 + c] = 0; return; }
     const unsigned long long* in = p.bucket_keys + (long long)img * kCandCap + lo;
     unsigned long long* sorted = p.sorted_keys + (long long)img * kCandCap + lo;
+    if (L > kClassSmemKeys) {
+        // long segment (up to kCandCap keys of one class): sorting it would cost O(L^2) (rank sort) for at most max_boxes picks;
+        // greedy selection by arg-max rounds instead: round r suppresses against the box picked in round r-1 and finds the
+        // best remaining key, <= max_boxes passes over the segment, alive bits in shared memory
+        __shared__ unsigned dead[kCandCap / 32];
+        const int words = (L + 31) >> 5;
+        for (int w = tid; w < words; w += kClassThreads) dead[w] = (w * 32 + 32 <= L) ? 0u : ~((1u << (L - w * 32)) - 1u);
+        __syncthreads();
+        const float4* bx = p.boxes + (long long)img * p.N;
+        unsigned long long* wk = p.win_keys + ((long long)img * p.nc + c) * p.max_boxes;
+        float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
+        int ns = 0;
+        while (ns < p.max_boxes) {
+            unsigned long long mine = ~0ull;
+            int mypos = 0;
+            for (int w = tid; w < words; w += kClassThreads) {
+                unsigned m = ~dead[w], kill = 0u;
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    const unsigned long long k = in[w * 32 + b];
+                    if (ns > 0 && iou_tf(bx[(int)(k & 0xFFFFFFull)], sel) > p.iou_thr) { kill |= 1u << b; continue; }   // strict >
+                    if (k < mine) { mine = k; mypos = w * 32 + b; }
+                }
+                dead[w] |= kill;
+            }
+            const unsigned long long best = block_min_u64<kClassThreads>(mine);
+            if (best == ~0ull) break;
+            const int box = (int)(best & 0xFFFFFFull);
+            if (mine == best) {                             // keys are unique: exactly one owner, and it owns that word of dead[]
+                wk[ns] = merge_key(c, __uint_as_float(~(unsigned)((best >> 24) & 0xFFFFFFFFull)), box);
+                dead[mypos >> 5] |= 1u << (mypos & 31);
+            }
+            sel = bx[box];
+            ns++;
+            __syncthreads();
+        }
+        if (tid == 0) p.nwin[img * 256 + c] = ns;
+        return;
+    }
     if (L <= kClassSmemKeys) {
         for (int i = tid; i < L; i += kClassThreads) sin[i] = in[i];
         __syncthreads();
@@ -248,6 +312,66 @@ __global__ void __launch_bounds__(kClassThreads) nms_class_kernel(NmsParams p) {
         }
     }
     if (lane == 0) p.nwin[img * 256 + c] = nsel;
+}
+
+// Exact path for images with more than kCandCap candidates (low score thresholds, e.g. mAP export at 0.001; TF's
+// CombinedNonMaxSuppression has no limit): one CTA per (image, class) works straight from the head tensors.  Pass 0 marks the
+// boxes whose class score passes the threshold (same arithmetic as decode_filter_kernel, so the same candidate set); then at
+// most max_boxes rounds, each ONE sweep over the still-alive boxes: suppress against the box selected in the previous round
+// (iou > thr strict) and find the best remaining (score desc, box asc) -- identical to TF's sorted greedy scan, without ever
+// materialising or sorting the candidate list.  Launched after nms_class_kernel on every step; returns at once for images
+// that fitted the fast path.
+constexpr int kOverflowThreads = 256;
+__global__ void __launch_bounds__(kOverflowThreads) nms_overflow_kernel(DecodeParams d, NmsParams p) {
+    extern __shared__ unsigned ov_dead[];                   // (N + 31) / 32 words: 1 = not a candidate / suppressed / selected
+    const int img = blockIdx.x / p.nc, c = blockIdx.x - img * p.nc;
+    if (p.cand_count[img] <= kCandCap) return;
+    const int tid = threadIdx.x;
+    const int words = (p.N + 31) >> 5;
+    auto class_score = [&](int n) {
+        int s, a, row, col;
+        const float* q = box_logits(d, img, n, s, a, row, col);
+        return __fmul_rn(sigmoid_rn(q[4]), sigmoid_rn(q[5 + c]));
+    };
+    for (int w = tid; w < words; w += kOverflowThreads) {
+        unsigned alive = 0u;
+        for (int b = 0; b < 32; b++) {
+            const int n = w * 32 + b;
+            if (n < p.N && class_score(n) > d.score_thr) alive |= 1u << b;      // strict >
+        }
+        ov_dead[w] = ~alive;
+    }
+    __syncthreads();
+    const float4* bx = p.boxes + (long long)img * p.N;      // decode_filter_kernel wrote every box that has a candidate
+    unsigned long long* wk = p.win_keys + ((long long)img * p.nc + c) * p.max_boxes;
+    float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
+    int ns = 0;
+    while (ns < p.max_boxes) {
+        unsigned long long best = ~0ull;
+        for (int w = tid; w < words; w += kOverflowThreads) {
+            unsigned m = ~ov_dead[w], kill = 0u;
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                const int n = w * 32 + b;
+                if (ns > 0 && iou_tf(bx[n], sel) > p.iou_thr) { kill |= 1u << b; continue; }
+                const unsigned long long k = ((unsigned long long)(~__float_as_uint(class_score(n))) << 32) | (unsigned long long)n;
+                best = k < best ? k : best;
+            }
+            ov_dead[w] |= kill;
+        }
+        best = block_min_u64<kOverflowThreads>(best);
+        if (best == ~0ull) break;
+        const int box = (int)(best & 0xFFFFFFFFull);
+        if (tid == 0) {
+            wk[ns] = merge_key(c, __uint_as_float(~(unsigned)(best >> 32)), box);
+            ov_dead[box >> 5] |= 1u << (box & 31);
+        }
+        sel = bx[box];
+        ns++;
+        __syncthreads();
+    }
+    if (tid == 0) p.nwin[img * 256 + c] = ns;
 }
 
 __global__ void __launch_bounds__(kMergeThreads) nms_merge_kernel(NmsParams p) {

@@ -102,7 +102,7 @@ struct y4_engine {
     int* d_cand_count = nullptr;
     float4* d_boxes = nullptr;
     float* d_out_boxes = nullptr; float* d_out_scores = nullptr; float* d_out_classes = nullptr;
-    int* d_out_valid = nullptr; int* d_out_idx = nullptr; int* d_overflow = nullptr;
+    int* d_out_valid = nullptr; int* d_out_idx = nullptr;
     bool weights_loaded = false;
     int64_t launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -115,7 +115,7 @@ struct y4_engine {
     int img_slot = 0;
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
-    char* stage[2] = {nullptr, nullptr};          // pinned: boxes | scores | classes | idx | valid | overflow
+    char* stage[2] = {nullptr, nullptr};          // pinned: boxes | scores | classes | idx | valid
     int64_t n_submitted = 0, n_collected = 0;
     int sub_batch[2] = {0, 0};
     // raw 8-bit input path (y4_predict_u8 / y4_submit_u8): device staging for the source images, one per input slot
@@ -406,8 +406,8 @@ void launch_spp(y4_engine* e, int batch) {
     else if (e->cfg.precision == Y4_PREC_FP16X3) spp_split_kernel<<<blocks, 256, 0, e->stream>>>(p, b.ptr_lo);
     else if (e->cfg.precision == Y4_PREC_FP16 && e->spp_C % kSppChunk == 0 && (size_t)b.H * b.W * 256 <= 200 * 1024) {
         const size_t smem = (size_t)b.H * b.W * 256;                    // x + three row-max tiles, 64 B per position each
-        static bool configured = false;
-        if (!configured) { cudaFuncSetAttribute(spp_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); configured = true; }
+        static DeviceOnce once;                                        // the attribute is per device
+        if (once.first_use()) cudaFuncSetAttribute(spp_sep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         spp_sep_kernel<<<(unsigned)(batch * (e->spp_C / kSppChunk)), 256, smem, e->stream>>>(p);
     } else if (e->cfg.precision == Y4_PREC_FP16 && e->spp_C % 8 == 0)
         spp_half8_kernel<<<(unsigned)((total / 8 + 255) / 256), 256, 0, e->stream>>>(p);
@@ -475,31 +475,27 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
     n.cand_keys = e->d_cand_keys; n.cand_count = e->d_cand_count; n.boxes = e->d_boxes;
     n.N = e->N; n.nc = nc; n.max_boxes = e->cfg.max_boxes; n.iou_thr = iou_thr;
     n.out_boxes = e->d_out_boxes; n.out_scores = e->d_out_scores; n.out_classes = e->d_out_classes;
-    n.out_valid = e->d_out_valid; n.out_idx = e->d_out_idx; n.overflow = e->d_overflow;
+    n.out_valid = e->d_out_valid; n.out_idx = e->d_out_idx;
     n.bucket_keys = e->d_bucket_keys; n.sorted_keys = e->d_sorted_keys; n.seg_start = e->d_seg_start;
     n.win_keys = e->d_win_keys; n.nwin = e->d_nwin;
     nms_bucket_kernel<<<batch, kBucketThreads, 0, e->stream>>>(n);
     nms_class_kernel<<<batch * nc, kClassThreads, 0, e->stream>>>(n);
+    // images with more than kCandCap candidates (none in the usual case: the CTAs return at once) are redone exactly, from the heads
+    nms_overflow_kernel<<<batch * nc, kOverflowThreads, sizeof(unsigned) * ((e->N + 31) / 32), e->stream>>>(d, n);
     nms_merge_kernel<<<batch, kMergeThreads, 0, e->stream>>>(n);
-    e->launches += 4;
+    e->launches += 5;
     CUDA_TRY(e, cudaGetLastError());
     return Y4_OK;
 }
 
 int fetch(y4_engine* e, int batch, float* boxes, float* scores, float* classes, int32_t* valid, int32_t* cand_idx) {
     const int mb = e->cfg.max_boxes;
-    int overflow = 0;
     if (boxes) CUDA_TRY(e, cudaMemcpyAsync(boxes, e->d_out_boxes, sizeof(float) * 4 * mb * batch, cudaMemcpyDeviceToHost, e->stream));
     if (scores) CUDA_TRY(e, cudaMemcpyAsync(scores, e->d_out_scores, sizeof(float) * mb * batch, cudaMemcpyDeviceToHost, e->stream));
     if (classes) CUDA_TRY(e, cudaMemcpyAsync(classes, e->d_out_classes, sizeof(float) * mb * batch, cudaMemcpyDeviceToHost, e->stream));
     if (valid) CUDA_TRY(e, cudaMemcpyAsync(valid, e->d_out_valid, sizeof(int) * batch, cudaMemcpyDeviceToHost, e->stream));
     if (cand_idx) CUDA_TRY(e, cudaMemcpyAsync(cand_idx, e->d_out_idx, sizeof(int) * mb * batch, cudaMemcpyDeviceToHost, e->stream));
-    CUDA_TRY(e, cudaMemcpyAsync(&overflow, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-    if (overflow) {
-        cudaMemsetAsync(e->d_overflow, 0, sizeof(int), e->stream);
-        return fail(e, Y4_ERR_CAPACITY, "more than Y4_MAX_CANDIDATES (8192) candidates above score_threshold in one image");
-    }
     return Y4_OK;
 }
 
@@ -643,6 +639,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     cudaEventCreate(&e->ev0); cudaEventCreate(&e->ev1);
     int rc = plan_graph(e);
     if (rc) return bail(rc);
+    if (e->N >= (1 << 24)) return bail(fail(e, Y4_ERR_ARG, "too many boxes per image for the 24-bit box field of the NMS keys"));
     const int S = cfg->img_size, B = cfg->max_batch, mb = cfg->max_boxes;
 #define CREATE_TRY(call) do { if ((call) != cudaSuccess) return bail(fail(e, Y4_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(cudaGetLastError()))); } while (0)
     CREATE_TRY(cudaMalloc(&e->d_img, sizeof(float) * 3 * S * S * B));
@@ -675,8 +672,6 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     CREATE_TRY(cudaMalloc(&e->d_out_classes, sizeof(float) * mb * B));
     CREATE_TRY(cudaMalloc(&e->d_out_valid, sizeof(int) * B));
     CREATE_TRY(cudaMalloc(&e->d_out_idx, sizeof(int) * mb * B));
-    CREATE_TRY(cudaMalloc(&e->d_overflow, sizeof(int)));
-    CREATE_TRY(cudaMemset(e->d_overflow, 0, sizeof(int)));
     e->flush_elems = (size_t)(192u << 20) / sizeof(float4);      // 192 MB > 126 MB L2
     CREATE_TRY(cudaMalloc(&e->d_flush, e->flush_elems * sizeof(float4)));
     // tcgen05 plans (tensor maps need the buffer addresses, which are now fixed)
@@ -871,7 +866,7 @@ void y4_destroy(y4_engine* e) {
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
     cudaFree(e->d_bucket_keys); cudaFree(e->d_sorted_keys); cudaFree(e->d_win_keys); cudaFree(e->d_seg_start); cudaFree(e->d_nwin);
     cudaFree(e->d_out_boxes); cudaFree(e->d_out_scores); cudaFree(e->d_out_classes);
-    cudaFree(e->d_out_valid); cudaFree(e->d_out_idx); cudaFree(e->d_overflow);
+    cudaFree(e->d_out_valid); cudaFree(e->d_out_idx);
     cudaFree(e->d_flush); cudaFree(e->d_gather);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -897,10 +892,13 @@ int y4_load_darknet(y4_engine* e, const char* path) {
     return y4_load_darknet_from_memory(e, buf.data(), buf.size());
 }
 
-static int ready(y4_engine* e, int batch, bool need_weights) {
+// Every entry point except y4_submit* / y4_collect uses input slot 0 and the shared result buffers, which belong to the batches
+// in flight while submits are outstanding.
+static int ready(y4_engine* e, int batch, bool need_weights, bool pipelined = false) {
     int rc = check_batch(e, batch);
     if (rc) return rc;
     if (need_weights && !e->weights_loaded) return fail(e, Y4_ERR_STATE, "weights not loaded (call y4_load_darknet first)");
+    if (!pipelined && e->n_submitted != e->n_collected) return fail(e, Y4_ERR_STATE, "y4_submit batches are in flight: y4_collect them first");
     cudaSetDevice(e->cfg.device);
     return Y4_OK;
 }
@@ -909,7 +907,6 @@ int y4_predict(y4_engine* e, const float* imgs, int32_t batch, float* boxes, flo
                int32_t* valid, int32_t* cand_idx) {
     int rc = ready(e, batch, true); if (rc) return rc;
     if (!imgs) return fail(e, Y4_ERR_ARG, "null imgs");
-    if (e->n_submitted != e->n_collected) return fail(e, Y4_ERR_STATE, "y4_submit batches are in flight: y4_collect them first");
     const size_t n = (size_t)batch * e->cfg.img_size * e->cfg.img_size * 3;
     CUDA_TRY(e, cudaMemcpyAsync(e->d_img, imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     rc = run_forward(e, batch); if (rc) return rc;
@@ -920,7 +917,6 @@ int y4_predict(y4_engine* e, const float* imgs, int32_t batch, float* boxes, flo
 int y4_forward_heads(y4_engine* e, const float* imgs, int32_t batch, float* hs, float* hm, float* hl) {
     int rc = ready(e, batch, true); if (rc) return rc;
     if (!imgs) return fail(e, Y4_ERR_ARG, "null imgs");
-    if (e->n_submitted != e->n_collected) return fail(e, Y4_ERR_STATE, "y4_submit batches are in flight: y4_collect them first");
     const size_t n = (size_t)batch * e->cfg.img_size * e->cfg.img_size * 3;
     CUDA_TRY(e, cudaMemcpyAsync(e->d_img, imgs, n * sizeof(float), cudaMemcpyHostToDevice, e->stream));
     rc = run_forward(e, batch); if (rc) return rc;
@@ -1106,7 +1102,7 @@ int y4_submit(y4_engine* e, const float* imgs, int32_t batch) {
 }
 
 static int submit_common(y4_engine* e, int32_t batch, const float* imgs, const uint8_t* const* u8, const int32_t* hs, const int32_t* ws, int reverse) {
-    int rc = ready(e, batch, true); if (rc) return rc;
+    int rc = ready(e, batch, true, true); if (rc) return rc;
     if (e->n_submitted - e->n_collected >= 2) return fail(e, Y4_ERR_STATE, "two batches already in flight: call y4_collect first");
     const int S = e->cfg.img_size, B = e->cfg.max_batch, mb = e->cfg.max_boxes;
     if (!e->copy_stream) {
@@ -1136,7 +1132,6 @@ static int submit_common(y4_engine* e, int32_t batch, const float* imgs, const u
     CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_out_classes, sizeof(float) * mb * batch, cudaMemcpyDeviceToHost, e->stream)); off += sizeof(float) * mb * B;
     CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_out_idx, sizeof(int) * mb * batch, cudaMemcpyDeviceToHost, e->stream)); off += sizeof(int) * mb * B;
     CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_out_valid, sizeof(int) * batch, cudaMemcpyDeviceToHost, e->stream)); off += sizeof(int) * B;
-    CUDA_TRY(e, cudaMemcpyAsync(st + off, e->d_overflow, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaEventRecord(e->ev_done[slot], e->stream));
     e->sub_batch[slot] = batch;
     e->n_submitted++;
@@ -1163,12 +1158,6 @@ int y4_collect(y4_engine* e, int32_t batch, float* boxes, float* scores, float* 
     if (cand_idx) memcpy(cand_idx, st + off, sizeof(int) * mb * batch);
     off += sizeof(int) * mb * B;
     if (valid) memcpy(valid, st + off, sizeof(int) * batch);
-    off += sizeof(int) * B;
-    int overflow = 0; memcpy(&overflow, st + off, sizeof(int));
-    if (overflow) {
-        cudaMemsetAsync(e->d_overflow, 0, sizeof(int), e->stream);
-        return fail(e, Y4_ERR_CAPACITY, "more than Y4_MAX_CANDIDATES (8192) candidates above score_threshold in one image");
-    }
     return Y4_OK;
 }
 

@@ -2,14 +2,15 @@
 
 Kept: ctor signature, predict / predict_img / predict_raw / predict_nonms / preprocess_img /
 export_prediction, the BGR/RGB behaviour of each method, and the DataFrame result shape.
-Dropped (out of scope): fit, Keras save/load, mAP evaluation, training model.
+Dropped (out of scope): fit, Keras save/load, training model.  `max_boxes` (config.py) sets both NMS sizes
+(per class and total), which the reference hard-codes to 100 = its default max_boxes (custom_layers.py:293-294).
 Generalised: grid = img_size // stride (the reference hard-codes 52/26/13, custom_layers.py:204-212).
 """
 import os
 
 import numpy as np
 
-from .binding import Engine, PREC_FP16, PREC_FP32
+from .binding import Engine, PREC_FP16, PREC_FP16X3, PREC_FP16_SIMT, PREC_FP32
 from .config import yolo_config
 from .utils import draw_bbox, get_detection_data, load_weights
 
@@ -34,7 +35,10 @@ class Yolov4(object):
         self.build_model(load_pretrained=bool(self.weight_path))
 
     def build_model(self, load_pretrained=True):
-        prec = PREC_FP32 if self.config.get('precision', 'fp16') == 'fp32' else PREC_FP16
+        precisions = {'fp32': PREC_FP32, 'fp16': PREC_FP16, 'fp16x3': PREC_FP16X3, 'fp16_simt': PREC_FP16_SIMT}
+        name = self.config.get('precision', 'fp16')
+        assert name in precisions, f'unknown precision {name!r} (one of {sorted(precisions)})'
+        prec = precisions[name]
         # one engine plays both Keras models: yolo_model (heads) and inference_model (heads + decode + NMS)
         self.engine = Engine(img_size=self.img_size[0], num_classes=self.num_classes,
                              max_batch=int(self.config.get('max_batch', 32)), precision=prec,
@@ -100,6 +104,18 @@ class Yolov4(object):
         detections = get_detection_data(img=raw_img, model_outputs=pred_output, class_names=self.class_names)
         draw_bbox(raw_img, detections, cmap=self.class_color, random_color=True)
         return detections
+
+    def export_gt(self, annotation_path, gt_folder_path):
+        """models.py:129-139: annotation lines `<img> x1,y1,x2,y2,cls ...` -> one `<class> <x1> <y1> <x2> <y2>` file per image
+        (the ground-truth side of eval_map; host only)."""
+        with open(annotation_path) as file:
+            for line in file:
+                parts = line.split(' ')
+                stem = parts[0].split(os.sep)[-1].split('.')[0]
+                with open(os.path.join(gt_folder_path, stem + '.txt'), 'w') as out:
+                    for obj in parts[1:]:
+                        x_min, y_min, x_max, y_max, class_id = [float(o) for o in obj.strip().split(',')]
+                        out.write(f'{self.class_names[int(class_id)]} {x_min} {y_min} {x_max} {y_max}\n')
 
     def export_prediction(self, annotation_path, pred_folder_path, img_folder_path, bs=2):
         """Batched caller (models.py:141-179): `<class> <score> <x1> <y1> <x2> <y2>` per detection, raw-image px.

@@ -54,7 +54,11 @@ def draw_bbox(img, detections, cmap, random_color=True, figsize=(10, 10), show_i
             cv2.rectangle(canvas, (x1 - line_width // 2, y1 - th), (x1 + tw, y1), color, cv2.FILLED)
             cv2.putText(canvas, label, (x1, y1), font, font_scale, (255, 255, 255), thickness, cv2.LINE_AA)
     if show_img:
-        import matplotlib.pyplot as plt      # lazy: matplotlib is optional in this image
+        try:
+            import matplotlib.pyplot as plt  # lazy: matplotlib is optional in this image
+        except ImportError:
+            print('draw_bbox: matplotlib is not installed, the annotated image is returned but not shown')
+            return canvas
         plt.figure(figsize=figsize)
         plt.imshow(canvas)
         plt.show()
