@@ -327,19 +327,13 @@ def main():
     peak_kind = 'burst' if near_max else 'sustained'
     peak_tf = pk['tflops_burst'] if near_max else pk['tflops_sustained']
     groups = {}
-    layers = eng.layers()
-    li = 0
-    for t in prof:
-        if li == 75 and len(prof) == len(layers) + 1 and 'spp' not in groups:
-            groups['spp'] = [1, float(t), 0.0]
-            continue
-        l = layers[li]; li += 1
+    for t, l in zip(prof, eng.steps()):                # one entry per launch of the forward, in schedule order
         if l['kernel_kind'] in (1, 2):
             nepi, lean = (4, 1) if l['tc_epi_warps'] == 44 else (l['tc_epi_warps'], 0)
             name = (f"conv_tc2_kernel<{l['tile_n']}, {nepi}>" if l['tc_mode'] == 4
-                    else f"conv_tc_kernel<{l['tile_n']}, {l['tc_bk']}, 0, {nepi}, {lean}>")
+                    else f"conv_tc_kernel<{l['tile_n']}, {l['tc_bk']}, {1 if args.precision == 'fp16x3' else 0}, {nepi}, {lean}>")
         else:
-            name = {4: 'conv0_tc_kernel', 3: 'conv0_direct_kernel', 0: 'conv_simt_kernel'}.get(l['kernel_kind'], 'other')
+            name = {5: 'spp_sep_kernel', 4: 'conv0_tc_kernel', 3: 'conv0_direct_kernel', 0: 'conv_simt_kernel'}.get(l['kernel_kind'], 'other')
         g = groups.setdefault(name, [0, 0.0, 0.0])
         g[0] += 1; g[1] += float(t); g[2] += l['flops'] * B
     top = max(groups, key=lambda k: groups[k][1])

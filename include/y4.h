@@ -26,10 +26,11 @@ extern "C" {
 #define Y4_ERR_CUDA         (-2)   /* CUDA runtime / driver failure, or no usable sm_100 device   */
 #define Y4_ERR_WEIGHTS      (-3)   /* darknet file has the wrong byte count (utils.py:50-53)      */
 #define Y4_ERR_STATE        (-4)   /* e.g. predict before weights were loaded                     */
-#define Y4_ERR_CAPACITY     (-5)   /* more (box,class) candidates above threshold than Y4_MAX_CANDIDATES */
+#define Y4_ERR_CAPACITY     (-5)   /* reserved (round 1: candidate-list overflow; no longer produced: images with more than
+                                      Y4_MAX_CANDIDATES candidates take an exact slower path, as TF has no limit)  */
 #define Y4_ERR_COMM         (-6)   /* NCCL failure                                                */
 
-#define Y4_MAX_CANDIDATES   8192   /* per image, after the score filter                           */
+#define Y4_MAX_CANDIDATES   8192   /* per image, after the score filter: capacity of the FAST NMS path         */
 
 /* conv-stack arithmetic.  Decode + NMS are always fp32. */
 #define Y4_PREC_FP32        0      /* fp32 activations, CUDA-core FFMA implicit GEMM (parity mode)          */
@@ -61,7 +62,8 @@ typedef struct y4_config {
 typedef struct y4_layer_info {
     int32_t idx, cin, cout, ksize, stride, batch_norm, activation /*0 linear,1 leaky,2 mish*/;
     int32_t out_hw;           /* output spatial size at the engine's img_size */
-    int32_t kernel_kind;      /* 0 = CUDA-core implicit GEMM, 1 = tcgen05 flat GEMM, 2 = tcgen05 strided-box */
+    int32_t kernel_kind;      /* 0 = CUDA-core implicit GEMM, 1 = tcgen05 flat GEMM, 2 = tcgen05 strided-box, 3 / 4 = conv 0 direct /
+                                 tcgen05; steps only: 5 = SPP max-pools, 6 = conv 0 + conv 1 fused (stem_tc.cuh, out_name "c0+c1") */
     int32_t tile_n;           /* N tile of the tcgen05 kernel (0 if kernel_kind==0) */
     int64_t flops;            /* 2*MAC per image */
     char    out_name[16];     /* name of the tensor this conv materialises (r<k> when the residual add is fused) */
@@ -136,7 +138,7 @@ int  y4_timer_end(y4_engine* e, float* ms);
 int  y4_flush_l2(y4_engine* e);
 /* Number of kernels this engine has launched since creation. */
 int64_t y4_launch_count(const y4_engine* e);
-/* Per-layer event timing of the last y4_profile_layers() call: ms[110 + 1 (spp) ] */
+/* Per-step CUDA-event timing of one forward: ms[y4_num_steps()], in schedule order (y4_describe_step). */
 int  y4_profile_layers(y4_engine* e, int32_t batch, float* ms, int32_t n);
 
 /* Pinned host memory for callers that want async H2D/D2H. */
@@ -161,6 +163,11 @@ void  y4_host_free(void* p);
 /* ---- introspection --------------------------------------------------------------------------------- */
 int  y4_num_layers(const y4_engine* e);
 int  y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info);
+/* The launch schedule of one forward (what y4_profile_layers times, in order): one entry per kernel launch.  A step is one of
+ * the 110 convs, a fused pair of sibling convs (csp_block's route / main 1x1, custom_layers.py:59-60: idx >= 110, out_name
+ * "c2+c3", flops of both), conv 0 + conv 1 in one kernel (kernel_kind 6, idx -2) or the SPP max-pools (kernel_kind 5, idx -1). */
+int  y4_num_steps(const y4_engine* e);
+int  y4_describe_step(const y4_engine* e, int32_t step, y4_layer_info* info);
 int64_t y4_num_boxes(const y4_engine* e);   /* N = 3 * sum(g^2) */
 /* Copy a named intermediate (e.g. "c0", "r1", "cat6", "c93") to host as unpadded NHWC float32
  * (batch,H,W,C); returns element count written, <0 on error.  out may be NULL to query the count. */

@@ -98,3 +98,64 @@ def test_dp_gather_equals_single_gpu_bitwise():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert 'bitwise: True' in r.stdout
+
+
+def test_sibling_fusion_is_bit_identical(weights):
+    """csp_block's route / main 1x1 convs (custom_layers.py:59-60) run as one GEMM with two destinations; every output bit must
+    equal the two separate convs (Y4_SIBLING=0)."""
+    import y4b200
+    import y4_oracle as O
+    W, blob = weights
+    size, batch = 160, 2
+    imgs = O.synth_images(0, 0, batch, size)
+    names = ['c2', 'c3', 'c9', 'c10', 'c18', 'c19', 'c39', 'c40', 'c60', 'c61', 'cat1', 'cat5']
+    res = {}
+    for tag, env in (('fused', None), ('separate', '0')):
+        os.environ.pop('Y4_SIBLING', None)
+        if env:
+            os.environ['Y4_SIBLING'] = env
+        try:
+            eng = y4b200.Engine(img_size=size, max_batch=batch, precision=y4b200.PREC_FP16)
+        finally:
+            os.environ.pop('Y4_SIBLING', None)
+        eng.load_darknet_bytes(blob)
+        heads = eng.forward_heads(imgs)
+        steps = eng.steps()
+        res[tag] = (heads + [eng.get_tensor(n, batch) for n in names], steps)
+        eng.close()
+    fused_steps = [s for s in res['fused'][1] if s['idx'] >= 110]
+    assert sorted(s['out_name'] for s in fused_steps) == ['c18+c19', 'c2+c3', 'c39+c40', 'c60+c61', 'c9+c10']
+    assert len(res['fused'][1]) == len(res['separate'][1]) - 5 == 106
+    assert all(s['kernel_kind'] == 1 and s['tc_epilogue'] in (32, 64) for s in fused_steps)
+    for a, b in zip(res['fused'][0], res['separate'][0]):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('size,batch', [(160, 2), (608, 2)])
+def test_stem_fusion_is_bit_identical(weights, size, batch):
+    """conv 0 + conv 1 in one kernel (stem_tc.cuh; conv 0's output never reaches HBM) == conv0_tc_kernel followed by conv 1's
+    tcgen05 plan (Y4_STEM=0), bit for bit: c1, a few tensors downstream, the heads."""
+    import y4b200
+    import y4_oracle as O
+    W, blob = weights
+    imgs = O.synth_images(0, 0, batch, size)
+    res = {}
+    for tag, env in (('stem', None), ('separate', '0')):
+        os.environ.pop('Y4_STEM', None)
+        if env:
+            os.environ['Y4_STEM'] = env
+        try:
+            eng = y4b200.Engine(img_size=size, max_batch=batch, precision=y4b200.PREC_FP16)
+        finally:
+            os.environ.pop('Y4_STEM', None)
+        eng.load_darknet_bytes(blob)
+        heads = eng.forward_heads(imgs)
+        res[tag] = (heads + [eng.get_tensor(n, batch) for n in ('c1', 'r1', 'c8')], eng.steps())
+        eng.close()
+    assert [s['out_name'] for s in res['stem'][1]][:1] == ['c0+c1'] and res['stem'][1][0]['kernel_kind'] == 6
+    assert len(res['stem'][1]) == len(res['separate'][1]) - 1
+    c1a, c1b = res['stem'][0][3], res['separate'][0][3]
+    assert c1a.shape == c1b.shape and np.abs(c1b).max() > 0
+    assert np.array_equal(c1a, c1b), float(np.abs(c1a - c1b).max())
+    for a, b in zip(res['stem'][0], res['separate'][0]):
+        assert np.array_equal(a, b)

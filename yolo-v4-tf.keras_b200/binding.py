@@ -39,7 +39,7 @@ EXPORTS = [
     'y4_load_darknet_from_memory', 'y4_predict', 'y4_predict_u8', 'y4_preprocess_u8', 'y4_submit', 'y4_submit_u8', 'y4_collect', 'y4_forward_heads', 'y4_decode_nms', 'y4_synth_fill',
     'y4_run_resident', 'y4_run_forward_resident', 'y4_run_decode_nms_resident', 'y4_upload_heads',
     'y4_fetch_results', 'y4_sync', 'y4_timer_begin', 'y4_timer_end', 'y4_flush_l2', 'y4_launch_count',
-    'y4_profile_layers', 'y4_host_alloc', 'y4_host_free', 'y4_num_layers', 'y4_describe_layer', 'y4_num_boxes',
+    'y4_profile_layers', 'y4_host_alloc', 'y4_host_free', 'y4_num_layers', 'y4_describe_layer', 'y4_num_steps', 'y4_describe_step', 'y4_num_boxes',
     'y4_debug_get_tensor', 'y4_debug_run_conv', 'y4_debug_trace_conv', 'y4_comm_unique_id', 'y4_comm_init', 'y4_allgather_results',
 ]
 
@@ -86,6 +86,8 @@ def load_library():
     lib.y4_host_free.argtypes = [vp]; lib.y4_host_free.restype = None
     lib.y4_num_layers.argtypes = [vp]
     lib.y4_describe_layer.argtypes = [vp, C.c_int32, C.POINTER(Y4LayerInfo)]
+    lib.y4_num_steps.argtypes = [vp]
+    lib.y4_describe_step.argtypes = [vp, C.c_int32, C.POINTER(Y4LayerInfo)]
     lib.y4_num_boxes.argtypes = [vp]; lib.y4_num_boxes.restype = C.c_int64
     lib.y4_debug_get_tensor.argtypes = [vp, C.c_char_p, C.c_int32, vp, C.c_int64]
     lib.y4_debug_get_tensor.restype = C.c_int64
@@ -312,6 +314,17 @@ class Engine:
         for i in range(self._lib.y4_num_layers(self._h)):
             li = Y4LayerInfo()
             self._chk(self._lib.y4_describe_layer(self._h, i, C.byref(li)))
+            d = {n: getattr(li, n) for n, _ in Y4LayerInfo._fields_}
+            d['out_name'] = d['out_name'].decode()
+            out.append(d)
+        return out
+
+    def steps(self):
+        """The launch schedule of one forward, in order (what profile_layers() times): convs, fused sibling pairs, SPP."""
+        out = []
+        for i in range(self._lib.y4_num_steps(self._h)):
+            li = Y4LayerInfo()
+            self._chk(self._lib.y4_describe_step(self._h, i, C.byref(li)))
             d = {n: getattr(li, n) for n, _ in Y4LayerInfo._fields_}
             d['out_name'] = d['out_name'].decode()
             out.append(d)

@@ -39,6 +39,9 @@ struct TcConvDesc {
     void* out; int out_ld, out_choff, out_f32, upsample;
     const void* res; int res_ld, res_choff;
     const __half* w16; const float* bias;
+    // sibling fusion: two convs that read the same input (csp_block's route / main 1x1, custom_layers.py:59-60) run as ONE GEMM
+    // with cout = 2C; output columns [0, split_col) go to `out`, columns [split_col, cout) to `out2` (slab epilogue only)
+    void* out2; int out2_ld, out2_choff, split_col;
     // pixel-pair view for a 3x3 stride-2 conv with cin = 32 (conv 1): two neighbouring pixels = 64 contiguous channels, so the taps
     // (kh, kw=0|1) are ONE 128 B-row box and (kh, kw=2|zero) another: 6 taps of 64 instead of 9 of 32 (w16_pair: [cout_pad][6*64])
     int pairx; const __half* w16_pair;
@@ -52,6 +55,8 @@ struct TcParams {
     CUtensorMap tmA_lo[4];       // split precision: low-order planes
     CUtensorMap tmW_lo;
     CUtensorMap tmOut;           // epi = 1: output slice as [rows][cout] fp16, box {32 channels, 32 rows}, SWIZZLE_64B (TMA store of the slabs)
+    CUtensorMap tmOut2;          // sibling fusion: second destination, for output columns >= split_col
+    int split_col;               // 0: single destination
     const float* bias;
     const float* wscale;         // per-cout 1/scale of the (power-of-two scaled) split weights, nullptr -> 1
     void* out;
@@ -557,7 +562,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
         for (int a = 0; a < 8; a++) { mbar_init(bar_pfull + 8u * a, 1); mbar_init(bar_pempty + 8u * a, 1); }
         mbar_init(bar_w, 1);
         if (p.mode == 3) tma_prefetch_desc(&p.tmA[1]);
-        if (p.epi) tma_prefetch_desc(&p.tmOut);
+        if (p.epi) { tma_prefetch_desc(&p.tmOut); if (p.split_col) tma_prefetch_desc(&p.tmOut2); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -926,7 +931,12 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                     }
                     fence_async_smem();
                     __syncwarp();
-                    if (lane == 0) { tma_store_2d(&p.tmOut, slab, tc.n0 + 32 * (k - h), (int)(tc.m0 + q * 32)); bulk_commit(); }
+                    if (lane == 0) {
+                        const int c0 = tc.n0 + 32 * (k - h);
+                        const bool second = p.split_col && c0 >= p.split_col;           // sibling fusion: the second conv's destination
+                        tma_store_2d(second ? &p.tmOut2 : &p.tmOut, slab, second ? c0 - p.split_col : c0, (int)(tc.m0 + q * 32));
+                        bulk_commit();
+                    }
                     sit++;
                 };
                 auto release_acc = [&]() { tc_fence_before(); if (lane == 0) mbar_arrive(bar_tempty + 8u * as); };
@@ -1203,6 +1213,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
             }
     }
     size_t epi_bytes = 0;
+    if (d.out2 && !epi) return 0;                              // two destinations: slab epilogue only
     if (nepi != 4 && (nepi != 8 || !(epi || d.split))) return 0;
     if (lean && (!epi || nepi != 4 || bn != 64 || d.split)) return 0;
     P.nepi = nepi; P.lean = lean;
@@ -1214,11 +1225,19 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
         p.epi = 1; p.epi_gw = gw;
         p.rows_alloc = (long long)d.max_batch * in_Hp * in_Wp;
         const int esz = d.out_f32 ? 4 : 2;
-        cuuint64_t dims[2] = {(cuuint64_t)p.cout_store, (cuuint64_t)p.rows_alloc};
+        cuuint64_t dims[2] = {(cuuint64_t)(d.out2 ? d.split_col : p.cout_store), (cuuint64_t)p.rows_alloc};
         cuuint64_t str[1] = {(cuuint64_t)d.out_ld * esz};
         cuuint32_t box[2] = {(cuuint32_t)gw, 32};
         char* out_base = reinterpret_cast<char*>(d.out) + (size_t)d.out_choff * esz;
         if (!encode_map(&p.tmOut, out_base, 2, dims, str, box, gw * esz, err, d.out_f32 != 0)) return -1;
+        if (d.out2) {
+            if (d.out_f32 || d.res || d.split_col % gw != 0 || (d.cout - d.split_col) % gw != 0) return 0;
+            cuuint64_t dims2[2] = {(cuuint64_t)(d.cout - d.split_col), (cuuint64_t)p.rows_alloc};
+            cuuint64_t str2[1] = {(cuuint64_t)d.out2_ld * esz};
+            char* out2_base = reinterpret_cast<char*>(d.out2) + (size_t)d.out2_choff * esz;
+            if (!encode_map(&p.tmOut2, out2_base, 2, dims2, str2, box, gw * esz, err, false)) return -1;
+            p.split_col = d.split_col;
+        }
         epi_bytes = epi_slab_bytes(nepi, d.out_f32 ? 64 : gw);
     }
     size_t wres_bytes = 0;

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmW);
         tma_prefetch_desc(&p.tmA[0]);
-        if (p.epi) tma_prefetch_desc(&p.tmOut);
+        if (p.epi) { tma_prefetch_desc(&p.tmOut); if (p.split_col) tma_prefetch_desc(&p.tmOut2); }
         if (p.mode == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
         for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 2 * NEPI); }
@@ -264,7 +264,12 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                 }
                 fence_async_smem();
                 __syncwarp();
-                if (lane == 0) { tma_store_2d(&p.tmOut, slab, n0 + 32 * (k - h), (int)(m0 + q * 32)); bulk_commit(); }
+                if (lane == 0) {
+                    const int c0 = n0 + 32 * (k - h);
+                    const bool second = p.split_col && c0 >= p.split_col;               // sibling fusion (conv_tc.cuh TcConvDesc::out2)
+                    tma_store_2d(second ? &p.tmOut2 : &p.tmOut, slab, second ? c0 - p.split_col : c0, (int)(m0 + q * 32));
+                    bulk_commit();
+                }
                 sit++;
             };
             auto release_acc = [&]() { tc_fence_before(); if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * as); };
@@ -361,6 +366,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     const int ntaps = d.pairx ? 6 : d.k * d.k;
     if (d.raw_in || cin % 64 != 0 || d.split || d.out_f32 || d.upsample) return 0;
     const bool box = d.stride == 2;
+    if (d.out2 && box) return 0;
     if (box ? (d.k != 3 || nepi != 4 || gw != 32) : (d.stride != 1)) return 0;
     if (d.cout_pad % bn || (nepi != 4 && nepi != 8)) return 0;
     if (!box && (d.cout % gw != 0 || (gw != 32 && (gw != 64 || nepi != 4)))) return 0;
@@ -397,11 +403,19 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
         cuuint64_t str[1] = {(cuuint64_t)d.in_ld * 2};
         cuuint32_t box2[2] = {64, 128};
         if (!encode_map(&p.tmA[0], in_base, 2, dims, str, box2, 128, err)) return -1;
-        cuuint64_t odims[2] = {(cuuint64_t)p.cout_store, (cuuint64_t)p.rows_alloc};
+        cuuint64_t odims[2] = {(cuuint64_t)(d.out2 ? d.split_col : p.cout_store), (cuuint64_t)p.rows_alloc};
         cuuint64_t ostr[1] = {(cuuint64_t)d.out_ld * 2};
         cuuint32_t obox[2] = {(cuuint32_t)gw, 32};
         char* out_base = reinterpret_cast<char*>(d.out) + (size_t)d.out_choff * 2;
         if (!encode_map(&p.tmOut, out_base, 2, odims, ostr, obox, gw * 2, err)) return -1;
+        if (d.out2) {
+            if (d.res || d.split_col % gw != 0 || (d.cout - d.split_col) % gw != 0) return 0;
+            cuuint64_t odims2[2] = {(cuuint64_t)(d.cout - d.split_col), (cuuint64_t)p.rows_alloc};
+            cuuint64_t ostr2[1] = {(cuuint64_t)d.out2_ld * 2};
+            char* out2_base = reinterpret_cast<char*>(d.out2) + (size_t)d.out2_choff * 2;
+            if (!encode_map(&p.tmOut2, out2_base, 2, odims2, ostr2, obox, gw * 2, err)) return -1;
+            p.split_col = d.split_col;
+        }
     } else {
         // output box TH x TW per CTA (<= 128 pixels), chosen for the most useful rows per tile; four parity-plane views of the input
         p.OH = d.OH; p.OW = d.OH;

@@ -30,6 +30,7 @@
 #include "conv_tc.cuh"
 #include "conv_tc2.cuh"
 #include "conv0_tc.cuh"
+#include "stem_tc.cuh"
 #include "preprocess.cuh"
 
 using namespace y4;
@@ -70,12 +71,14 @@ struct ConvOp {
     float* d_wscale = nullptr;  // split precision: 1/s per cout (exact)
     __half* d_w16k32 = nullptr; // conv 0 only: [32][32], K zero-padded 27 -> 32 (conv0_tc.cuh)
     __half* d_w16_pair = nullptr; // 3x3 stride-2 conv with cin = 32 (conv 1): [cout_pad][6*64] for the pixel-pair view (TcConvDesc::pairx)
+    int fused_a = -1, fused_b = -1;   // >= 0: this entry is the sibling fusion of convs a and b (same input, one GEMM, cout = 2C):
+    View out2;                        // columns [0, C) -> out (= a's destination), [C, 2C) -> out2 (= b's); appended after the 110 real convs
     int kind = 0;              // 0 simt, 1 tc flat, 2 tc box
     TcConvPlan tc;             // tensor maps + tile config (conv_tc.cuh)
     TcConvDesc desc{};         // what tc was planned from (the autotuner re-plans candidates from it)
     std::string out_name;
 };
-struct Step { int type; int conv; };   // type 0 conv, 1 spp
+struct Step { int type; int conv; };   // type 0 conv (or fused sibling pair), 1 spp, 3 stem (conv 0 + conv 1 in one kernel)
 
 }  // namespace
 
@@ -88,6 +91,7 @@ struct y4_engine {
     std::map<std::string, View> views;
     std::vector<ConvOp> convs;
     std::vector<Step> steps;
+    StemPlan stem;                     // conv 0 + conv 1 fused (stem_tc.cuh), when eligible
     View spp_view;                     // concat buffer view of the SPP
     int spp_C = 0;
     float* d_img = nullptr;
@@ -359,6 +363,31 @@ int plan_graph(y4_engine* e) {
             e->views[o.out] = placed[o.out];
         }
     }
+    // Sibling fusion (tcgen05 fp16 mode): csp_block's route and main 1x1 convs read the same tensor (custom_layers.py:59-60:
+    // c2|c3, c9|c10, c18|c19, c39|c40, c60|c61).  They run as ONE GEMM with the two weight matrices stacked along N: the input is
+    // read once and the N tile doubles; the epilogue stores the two halves to their own destinations.  Same K order and the same
+    // per-element arithmetic as the separate convs, so the outputs are bit-identical (tests/test_gpu_determinism.py).
+    const bool fuse = e->cfg.precision == Y4_PREC_FP16 && !(getenv("Y4_SIBLING") && getenv("Y4_SIBLING")[0] == '0');
+    if (fuse) {
+        const size_t nreal = e->convs.size();
+        for (size_t i = 0; i + 1 < nreal; i++) {
+            const ConvOp a = e->convs[i], b = e->convs[i + 1];
+            const bool same_in = a.in.buf == b.in.buf && a.in.choff == b.in.choff && a.in.C == b.in.C && !a.raw_in;
+            if (!same_in || a.k != 1 || b.k != 1 || a.stride != 1 || b.stride != 1 || a.cout != b.cout || a.act != b.act || !a.bn || !b.bn ||
+                a.has_res || b.has_res || a.upsample || b.upsample || a.out_f32 || b.out_f32 || a.cout % 64 != 0) continue;
+            ConvOp f = a;
+            f.idx = (int)e->convs.size(); f.cout = 2 * a.cout; f.cout_pad = 2 * a.cout; f.out2 = b.out;
+            f.fused_a = (int)i; f.fused_b = (int)i + 1;
+            f.out_name = a.out_name + "+" + b.out_name;
+            e->convs.push_back(f);
+            const int fi = (int)e->convs.size() - 1;
+            for (size_t k = 0; k < e->steps.size(); k++)
+                if (e->steps[k].type == 0 && e->steps[k].conv == (int)i) e->steps[k].conv = fi;
+            for (size_t k = 0; k < e->steps.size(); k++)
+                if (e->steps[k].type == 0 && e->steps[k].conv == (int)i + 1) { e->steps.erase(e->steps.begin() + k); break; }
+            i++;
+        }
+    }
     for (int i = 0; i < 3; i++) {
         e->head_buf[i] = e->views[heads[i]].buf;
         e->g[i] = S / e->cfg.strides[i];
@@ -442,11 +471,19 @@ int run_conv(y4_engine* e, const ConvOp& c, int batch) {
     return Y4_OK;
 }
 
-int run_forward(y4_engine* e, int batch) {
-    for (auto& s : e->steps) {
-        if (s.type == 0) { int rc = run_conv(e, e->convs[s.conv], batch); if (rc) return rc; }
-        else launch_spp(e, batch);
+int run_step(y4_engine* e, const Step& s, int batch) {
+    if (s.type == 0) return run_conv(e, e->convs[s.conv], batch);
+    if (s.type == 3) {
+        if (stem_launch(e->stem, e->d_img, batch, e->stream) != 0) return fail(e, Y4_ERR_CUDA, "stem (conv 0 + conv 1) launch failed");
+        e->launches++;
+        return Y4_OK;
     }
+    launch_spp(e, batch);
+    return Y4_OK;
+}
+
+int run_forward(y4_engine* e, int batch) {
+    for (auto& s : e->steps) { int rc = run_step(e, s, batch); if (rc) return rc; }
     CUDA_TRY(e, cudaGetLastError());
     return Y4_OK;
 }
@@ -508,13 +545,14 @@ int check_batch(y4_engine* e, int batch) {
 int upload_weights(y4_engine* e, const unsigned char* data, size_t nbytes) {
     // utils.py:12-53: 5 x int32 header, then per conv [beta,gamma,mean,var | bias] + OIHW weights
     size_t need = 20;
-    for (auto& c : e->convs) need += 4ull * ((c.bn ? 4 * c.cout : c.cout) + (size_t)c.cout * c.cin * c.k * c.k);
+    for (auto& c : e->convs) if (c.fused_a < 0) need += 4ull * ((c.bn ? 4 * c.cout : c.cout) + (size_t)c.cout * c.cin * c.k * c.k);
     if (nbytes != need)
         return fail(e, Y4_ERR_WEIGHTS, "darknet weights: expected " + std::to_string(need) + " bytes, got " + std::to_string(nbytes));
     size_t off = 20;
     std::vector<float> w32, bias;
     std::vector<__half> w16;
     for (auto& c : e->convs) {
+        if (c.fused_a >= 0) continue;                       // built from its two halves below
         const float* f = reinterpret_cast<const float*>(data + off);
         std::vector<double> scale(c.cout, 1.0);
         bias.assign(c.cout_pad, 0.f);
@@ -586,6 +624,15 @@ int upload_weights(y4_engine* e, const unsigned char* data, size_t nbytes) {
         }
         CUDA_TRY(e, cudaMemcpy(c.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
     }
+    for (auto& c : e->convs) {
+        if (c.fused_a < 0) continue;                        // sibling fusion: stack the two folded weight matrices / biases along N
+        const ConvOp &a = e->convs[c.fused_a], &b = e->convs[c.fused_b];
+        const size_t wn = (size_t)a.cout * a.K;
+        CUDA_TRY(e, cudaMemcpy(c.d_w16, a.d_w16, wn * 2, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaMemcpy(c.d_w16 + wn, b.d_w16, wn * 2, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaMemcpy(c.d_bias, a.d_bias, a.cout * 4, cudaMemcpyDeviceToDevice));
+        CUDA_TRY(e, cudaMemcpy(c.d_bias + a.cout, b.d_bias, a.cout * 4, cudaMemcpyDeviceToDevice));
+    }
     e->weights_loaded = true;
     return Y4_OK;
 }
@@ -645,6 +692,11 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     CREATE_TRY(cudaMalloc(&e->d_img, sizeof(float) * 3 * S * S * B));
     e->d_img_slot[0] = e->d_img;
     for (auto& c : e->convs) {
+        if (c.fused_a >= 0) {                               // tcgen05 only: fp16 weights + bias
+            CREATE_TRY(cudaMalloc(&c.d_w16, sizeof(__half) * c.K * c.cout_pad));
+            CREATE_TRY(cudaMalloc(&c.d_bias, sizeof(float) * c.cout_pad));
+            continue;
+        }
         CREATE_TRY(cudaMalloc(&c.d_w32, sizeof(float) * c.K * c.cout_pad));
         CREATE_TRY(cudaMalloc(&c.d_w16, sizeof(__half) * c.K * c.cout_pad));
         if (!c.raw_in && c.cin == 32 && c.k == 3 && c.stride == 2) CREATE_TRY(cudaMalloc(&c.d_w16_pair, sizeof(__half) * 384 * c.cout_pad));
@@ -686,6 +738,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             d.out = ob.ptr; d.out_ld = ob.C; d.out_choff = c.out.choff; d.out_f32 = c.out_f32; d.upsample = c.upsample;
             if (c.has_res) { const Buf& rb = e->bufs[c.res.buf]; d.res = rb.ptr; d.res_ld = rb.C; d.res_choff = c.res.choff; }
             d.w16 = c.d_w16; d.bias = c.d_bias; d.w16_pair = split ? nullptr : c.d_w16_pair;
+            if (c.fused_a >= 0) { const Buf& ob2 = e->bufs[c.out2.buf]; d.out2 = ob2.ptr; d.out2_ld = ob2.C; d.out2_choff = c.out2.choff; d.split_col = c.cout / 2; }
             if (split) {
                 d.split = 1; d.w16_lo = c.d_w16_lo; d.wscale = c.d_wscale; d.out_lo = ob.ptr_lo;
                 if (!c.raw_in) d.in_lo = e->bufs[c.in.buf].ptr_lo;
@@ -698,10 +751,27 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                 c.kind = (c0 && c0[0] == 'd') || !c.d_w16k32 || split ? 3 : 4;   // split precision: fp32 direct conv writing hi + lo
                 continue;
             }
-            int kind = tc_plan(d, &c.tc, &terr);
+            int kind = c.fused_a >= 0 ? tc_plan(d, &c.tc, &terr, 0, 99, 0, 1, /*epi*/ 1, 4, 0, 32, 0) : tc_plan(d, &c.tc, &terr);
+            if (c.fused_a >= 0 && kind != 1) return bail(fail(e, Y4_ERR_CUDA, "tcgen05 plan failed for fused conv " + c.out_name + ": " + terr));
             if (kind < 0) return bail(fail(e, Y4_ERR_CUDA, "tcgen05 plan failed for conv " + std::to_string(c.idx) + ": " + terr));
             c.kind = kind;
             c.desc = d;
+        }
+        // conv 0 + conv 1 as one kernel (stem_tc.cuh): conv 0's output never reaches HBM.  Y4_STEM=0 keeps the two kernels.
+        if (!split && !(getenv("Y4_STEM") && getenv("Y4_STEM")[0] == '0') && e->convs.size() > 1) {
+            ConvOp &c0 = e->convs[0], &c1 = e->convs[1];
+            const bool shape_ok = c0.kind == 4 && c0.d_w16k32 && c1.cin == 32 && c1.cout == 64 && c1.k == 3 && c1.stride == 2 && c1.act == ACT_LEAKY &&
+                                  c0.act == ACT_LEAKY && !c1.has_res && !c1.upsample && !c1.out_f32 && c1.in.buf == c0.out.buf && c1.fused_a < 0;
+            if (shape_ok) {
+                const Buf& ob = e->bufs[c1.out.buf];
+                std::string serr;
+                if (stem_plan(&e->stem, c0.d_bias, c0.d_w16k32, c1.d_bias, c1.d_w16, ob.ptr, ob.C, c1.out.choff, S, B, &serr)) {
+                    for (size_t k = 0; k < e->steps.size(); k++)
+                        if (e->steps[k].type == 0 && e->steps[k].conv == 0) e->steps[k] = Step{3, -1};
+                    for (size_t k = 0; k < e->steps.size(); k++)
+                        if (e->steps[k].type == 0 && e->steps[k].conv == 1) { e->steps.erase(e->steps.begin() + k); break; }
+                }
+            }
         }
         // Plan-time autotune, IN CONTEXT: every candidate configuration is planned for all layers it applies to, the whole
         // forward runs with per-layer CUDA events, and each layer keeps the plan that was fastest where it actually sits
@@ -783,7 +853,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                             const int rc2 = run_conv(e, c, B);
                             c.tc = keep;
                             if (rc2) { cudaGetLastError(); if (ok[st.conv]) ok[st.conv] = 2; }          // 2: launch refused
-                        } else launch_spp(e, B);
+                        } else if (run_step(e, st, B)) cudaGetLastError();
                         cudaEventRecord(ev[i + 1], e->stream);
                     }
                     if (cudaStreamSynchronize(e->stream) != cudaSuccess) return false;
@@ -1194,8 +1264,7 @@ int y4_profile_layers(y4_engine* e, int32_t batch, float* ms, int32_t n) {
     cudaEventRecord(ev[0], e->stream);
     for (size_t i = 0; i < e->steps.size(); i++) {
         auto& s = e->steps[i];
-        if (s.type == 0) { rc = run_conv(e, e->convs[s.conv], batch); if (rc) return rc; }
-        else launch_spp(e, batch);
+        rc = run_step(e, s, batch); if (rc) return rc;
         cudaEventRecord(ev[i + 1], e->stream);
     }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
@@ -1207,7 +1276,13 @@ int y4_profile_layers(y4_engine* e, int32_t batch, float* ms, int32_t n) {
 void* y4_host_alloc(size_t nbytes) { void* p = nullptr; return cudaHostAlloc(&p, nbytes, cudaHostAllocDefault) == cudaSuccess ? p : nullptr; }
 void y4_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-int y4_num_layers(const y4_engine* e) { return e ? (int)e->convs.size() : 0; }
+int y4_num_layers(const y4_engine* e) {                 // the 110 convs of the reference (fused sibling entries come after them)
+    if (!e) return 0;
+    int n = 0;
+    for (auto& c : e->convs) n += c.fused_a < 0;
+    return n;
+}
+int y4_num_steps(const y4_engine* e) { return e ? (int)e->steps.size() : 0; }
 int64_t y4_num_boxes(const y4_engine* e) { return e ? e->N : 0; }
 
 int y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info) {
@@ -1225,6 +1300,31 @@ int y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info) {
     return Y4_OK;
 }
 
+int y4_describe_step(const y4_engine* e, int32_t step, y4_layer_info* info) {
+    if (!e || !info || step < 0 || step >= (int)e->steps.size()) return Y4_ERR_ARG;
+    const Step& st = e->steps[step];
+    if (st.type == 0) {
+        int rc = y4_describe_layer(e, st.conv, info);
+        if (rc) return rc;
+        const ConvOp& c = e->convs[st.conv];
+        if (c.fused_a >= 0) info->flops = 2ll * c.N_OH * c.N_OH * c.cout * c.K;
+        return Y4_OK;
+    }
+    memset(info, 0, sizeof(*info));
+    if (st.type == 3) {                                     // conv 0 + conv 1 in one kernel
+        const ConvOp &c0 = e->convs[0], &c1 = e->convs[1];
+        info->idx = -2; info->kernel_kind = 6; info->cin = c0.cin; info->cout = c1.cout; info->ksize = 3; info->stride = 2;
+        info->batch_norm = 1; info->activation = c1.act; info->out_hw = c1.N_OH; info->tile_n = 64;
+        info->flops = 2ll * c0.N_OH * c0.N_OH * c0.cout * c0.K + 2ll * c1.N_OH * c1.N_OH * c1.cout * c1.K;
+        snprintf(info->out_name, sizeof(info->out_name), "c0+c1");
+        return Y4_OK;
+    }
+    info->idx = -1; info->kernel_kind = 5;                  // SPP max-pools
+    info->out_hw = e->bufs[e->spp_view.buf].H; info->cin = info->cout = e->spp_C;
+    snprintf(info->out_name, sizeof(info->out_name), "spp");
+    return Y4_OK;
+}
+
 int y4_debug_run_conv(y4_engine* e, int32_t idx, int32_t batch, int32_t use_tc) {
     int rc = ready(e, batch, true); if (rc) return rc;
     if (idx < 0 || idx >= (int)e->convs.size()) return fail(e, Y4_ERR_ARG, "bad conv idx");
@@ -1234,6 +1334,7 @@ int y4_debug_run_conv(y4_engine* e, int32_t idx, int32_t batch, int32_t use_tc) 
         rc = run_conv(e, c, batch); if (rc) return rc;
     } else {
         if (e->cfg.precision == Y4_PREC_FP16X3) return fail(e, Y4_ERR_ARG, "no CUDA-core kernel for split-precision buffers");
+        if (c.fused_a >= 0) return fail(e, Y4_ERR_ARG, "fused sibling convs have no CUDA-core kernel: run the two convs");
         launch_simt(e, c, batch);
     }
     CUDA_TRY(e, cudaGetLastError());
