@@ -330,7 +330,7 @@ def main():
     for t, l in zip(prof, eng.steps()):                # one entry per launch of the forward, in schedule order
         if l['kernel_kind'] in (1, 2):
             nepi, lean = (4, 1) if l['tc_epi_warps'] == 44 else (l['tc_epi_warps'], 0)
-            name = (f"conv_tc2_kernel<{l['tile_n']}, {nepi}>" if l['tc_mode'] == 4
+            name = (f"conv_tc2_kernel<{l['tile_n']}, {nepi}>" if l['tc_mode'] in (4, 5)
                     else f"conv_tc_kernel<{l['tile_n']}, {l['tc_bk']}, {1 if args.precision == 'fp16x3' else 0}, {nepi}, {lean}>")
         else:
             name = {5: 'spp_sep_kernel', 4: 'conv0_tc_kernel', 3: 'conv0_direct_kernel', 0: 'conv_simt_kernel'}.get(l['kernel_kind'], 'other')

@@ -67,7 +67,7 @@ typedef struct y4_layer_info {
     int32_t tile_n;           /* N tile of the tcgen05 kernel (0 if kernel_kind==0) */
     int64_t flops;            /* 2*MAC per image */
     char    out_name[16];     /* name of the tensor this conv materialises (r<k> when the residual add is fused) */
-    int32_t tc_mode;          /* tcgen05 plan: 1 flat (one TMA per tap), 2 strided box, 3 flat with A-patch reuse, 4 flat CTA pair (cta_group::2) */
+    int32_t tc_mode;          /* tcgen05 plan: 1 flat (one TMA per tap), 2 strided box, 3 flat with A-patch reuse, 4 CTA pair (cta_group::2), 5 CTA pair with A-patch reuse */
     int32_t tc_epilogue;      /* 0 per-thread global stores; 32 / 64: swizzled smem slab + TMA store in groups of that many channels */
     int32_t tc_stages, tc_group, tc_ctas_per_sm, tc_bk;   /* ring depth, k-blocks per barrier, persistent CTAs per SM, K block */
     int32_t tc_epi_warps;     /* 4 or 8 epilogue warps; 44 = four warps, lean variant compiled for up to four CTAs per SM */

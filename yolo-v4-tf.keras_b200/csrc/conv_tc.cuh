@@ -193,6 +193,32 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Elect-predicated forms for WARP-UNIFORM issue loops: all 32 lanes of the TMA / MMA warp run the loop and one elected lane
+// issues.  Inside `if (lane == 0) { loop }` every value is a per-thread (vector) value to ptxas, and each UTCHMMA / UTMALDG
+// (whose operands are uniform registers) was preceded by five R2UR moves and a BRA.U.ANY convergence loop: ~100 issue cycles per
+// MMA against 32-64 tensor cycles at N <= 128 (measured: the 3x3 layers gained 12-17 % from this change alone).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void umma_f16_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -581,11 +607,12 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
 
     if (warp == 0) {
         // ===== TMA producer: the stage ring runs straight across tile boundaries =====
-        if (lane == 0) {
+        {                                                   // all 32 lanes run the loops (warp-uniform), lane 0 issues
+            const bool leader = lane == 0;
             const uint32_t a_bytes = p.mode == 1 ? (uint32_t)A_BYTES : (uint32_t)(p.TH * p.TW * BK * 2);
             uint32_t it = 0;
             long long w_empty = 0;
-            if (p.mode == 3) {
+            if (p.mode == 3) { if (leader) {
                 // A patches: one patch feeds patch_taps taps through row-shifted UMMA descriptors.  patch_taps = 9: rows
                 // m0 - Wp - 1 .. cover the whole 3x3 halo (pays when Wp is small); patch_taps = 3: one patch per kernel row kh,
                 // rows m0 + (kh-1)*Wp - 1 .. +130, feeding kw = 0,1,2 (A traffic 3x instead of 9x whatever Wp is).
@@ -640,8 +667,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                     }
                     if (j == 0) Y4_STAMP(3);
                 }
-            } else {
-            if (p.bres) {
+            } } else {
+            if (p.bres && leader) {
                 // the whole weight matrix (n_tiles == 1) stays in shared memory for the life of the CTA: num_kb boxes, one barrier
                 mbar_expect_tx(bar_w, (uint32_t)p.num_kb * (uint32_t)B_BYTES);
                 for (int kb = 0; kb < p.num_kb; kb++) {
@@ -661,6 +688,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                     mbar_wait_t(bar_empty + 8u * s, ph ^ 1u, dbg ? &w_empty : nullptr);
                     const uint32_t fb = bar_full + 8u * s;
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
+                    if (leader) {
                     mbar_expect_tx(fb, (uint32_t)gcount * (a_bytes + (p.bres ? 0u : (uint32_t)B_BYTES)) * (SPLIT ? 2u : 1u));
                     for (int kk = 0; kk < gcount; kk++) {
                         const int kb = kb0 + kk;
@@ -697,16 +725,18 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                             tma_load_2d(sl + A_BYTES, &p.tmW_lo, fb, wcol, tc.n0);
                         }
                     }
-                    if (it == 0) Y4_STAMP(2);
+                    }
+                    __syncwarp();
+                    if (it == 0 && leader) Y4_STAMP(2);
                 }
-                if (tile == (int)blockIdx.x) Y4_STAMP(3);
+                if (tile == (int)blockIdx.x && leader) Y4_STAMP(3);
             }
             }
-            if (dbg) dbg[12] = w_empty;
+            if (dbg && leader) dbg[12] = w_empty;
         }
     } else if (warp == 1) {
         // ===== MMA issuer: accumulator stage = tile parity =====
-        if (lane == 0) {
+        {                                                   // all 32 lanes run the loops; MMAs and commits are elect-predicated
             uint32_t it = 0, ti = 0, pit = 0;
             long long w_full = 0, w_tempty = 0, w_pfull = 0;
             const long long t_mma0 = clock64();
@@ -726,7 +756,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                         const uint32_t ph = (it / (uint32_t)S) & 1u;
                         mbar_wait_t(bar_full + 8u * s, ph, dbg ? &w_full : nullptr);
                         tc_fence_after();
-                        if (it == 0) Y4_STAMP(4);
+                        if (it == 0 && lane == 0) Y4_STAMP(4);
                         const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
                         for (int kk = 0; kk < gcount; kk++) {
                             const int kb = kb0 + kk;
@@ -741,16 +771,16 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                             const uint64_t lb = make_smem_desc<SWZ>(sa + STAGE_BYTES + A_BYTES);
                             // (a_hi + a_lo)(b_hi + b_lo) without the a_lo*b_lo term (2^-22 relative)
 #pragma unroll
-                            for (int k = 0; k < BK / 16; k++) umma_f16(tacc, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (cpos | k) ? 1u : 0u);
+                            for (int k = 0; k < BK / 16; k++) umma_f16_elect(tacc, la + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (cpos | k) ? 1u : 0u);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; k++) umma_f16(tacc, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), IDESC, 1u);
+                            for (int k = 0; k < BK / 16; k++) umma_f16_elect(tacc, da + (uint64_t)(2 * k), lb + (uint64_t)(2 * k), IDESC, 1u);
 #pragma unroll
-                            for (int k = 0; k < BK / 16; k++) umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, 1u);
-                            if (cpos == CH - 1 || kb == p.num_kb - 1) { umma_commit(bar_tfull + 8u * as); ci++; }   // partial complete
+                            for (int k = 0; k < BK / 16; k++) umma_f16_elect(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, 1u);
+                            if (cpos == CH - 1 || kb == p.num_kb - 1) { umma_commit_elect(bar_tfull + 8u * as); ci++; }   // partial complete
                         }
-                        umma_commit(bar_empty + 8u * s);
+                        umma_commit_elect(bar_empty + 8u * s);
                     }
-                    if (ti == 0) Y4_STAMP(5);
+                    if (ti == 0 && lane == 0) Y4_STAMP(5);
                 }
             } else
             for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ti++) {
@@ -777,7 +807,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                                 tc_fence_after();
                                 bsm = bring + s * (uint32_t)B_BYTES;
                             }
-                            if (cb == 0 && tap == 0 && ti == 0) Y4_STAMP(4);
+                            if (cb == 0 && tap == 0 && ti == 0 && lane == 0) Y4_STAMP(4);
                             // full patch: row 0 is output row m0 shifted by -(Wp+1), tap (kh,kw) starts at row kh*Wp + kw;
                             // row patch: row 0 is m0 + (kh-1)*Wp - 1, tap kw starts at row kw
                             const int roff = PT == 9 ? (tap / 3) * p.Wp + (tap % 3) : t;
@@ -785,10 +815,10 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                             const uint64_t db = make_smem_desc<SWZ>(bsm);
 #pragma unroll
                             for (int k = 0; k < BK / 16; k++)
-                                umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (cb | tap | k) ? 1u : 0u);
-                            if (!p.bres) { umma_commit(bar_empty + 8u * (it % (uint32_t)S)); it++; }
+                                umma_f16_elect(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (cb | tap | k) ? 1u : 0u);
+                            if (!p.bres) { umma_commit_elect(bar_empty + 8u * (it % (uint32_t)S)); it++; }
                         }
-                        umma_commit(bar_pempty + 8u * ps);      // all taps of this patch have been read
+                        umma_commit_elect(bar_pempty + 8u * ps);      // all taps of this patch have been read
                     }
                 } else
                 for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
@@ -796,7 +826,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                     const uint32_t ph = (it / (uint32_t)S) & 1u;
                     mbar_wait_t(bar_full + 8u * s, ph, dbg ? &w_full : nullptr);
                     tc_fence_after();
-                    if (it == 0) Y4_STAMP(4);
+                    if (it == 0 && lane == 0) Y4_STAMP(4);
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
                     for (int kk = 0; kk < gcount; kk++) {
                         const uint32_t sa = ring0 + (s * (uint32_t)G + (uint32_t)kk) * ASTRIDE;
@@ -804,14 +834,14 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) co
                         const uint64_t db = make_smem_desc<SWZ>(p.bres ? base + (uint32_t)(kb0 + kk) * (uint32_t)B_BYTES : sa + A_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / 16; k++)
-                            umma_f16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
+                            umma_f16_elect(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
                     }
-                    umma_commit(bar_empty + 8u * s);        // frees this smem stage once the MMAs have read it
+                    umma_commit_elect(bar_empty + 8u * s);        // frees this smem stage once the MMAs have read it
                 }
-                umma_commit(bar_tfull + 8u * as);           // accumulator complete
-                if (ti == 0) Y4_STAMP(5);
+                umma_commit_elect(bar_tfull + 8u * as);           // accumulator complete
+                if (ti == 0 && lane == 0) Y4_STAMP(5);
             }
-            if (dbg) { dbg[9] = w_full; dbg[10] = w_tempty; dbg[11] = clock64() - t_mma0; dbg[13] = w_pfull; }
+            if (dbg && lane == 0) { dbg[9] = w_full; dbg[10] = w_tempty; dbg[11] = clock64() - t_mma0; dbg[13] = w_pfull; }
         }
     } else {
         // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31; with NEPI = 8, warps w and w+4 alternate 32-column groups =====

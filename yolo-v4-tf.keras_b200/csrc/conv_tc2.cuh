@@ -57,6 +57,24 @@ __device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, u
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
         "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
 }
+// elect-predicated issue for warp-uniform loops (see elect_one in conv_tc.cuh)
+__device__ __forceinline__ void umma_f16_cg2_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p, e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred e;\n\t"
+        "elect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+        "}" ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {       // from either CTA of the pair
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
 }
@@ -74,12 +92,17 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     const uint32_t raw = smem_u32(tc_smem);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const int S = p.stages, G = p.group;
-    const uint32_t ring_bytes = (uint32_t)(S * G) * (uint32_t)STAGE_BYTES;
+    // mode 3 (3x3 stride 1, A-patch reuse): [patch_slots patches][S stages of this CTA's half B tile]; otherwise S*G stages of (A | B)
+    const bool patch = p.mode == 3;
+    const uint32_t ring_bytes = patch ? (uint32_t)(p.patch_slots * p.patch_bytes) + (uint32_t)S * (uint32_t)B_BYTES
+                                      : (uint32_t)(S * G) * (uint32_t)STAGE_BYTES;
+    const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);   // mode 3: first B stage
     const uint32_t epi_bytes = p.epi ? epi_slab_bytes(NEPI, p.epi_gw) : 0u;
     const uint32_t slabs = base + ring_bytes;
     const uint32_t bars = slabs + epi_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
     const uint32_t tmem_slot = bars + 16u * S + 32u;
+    const uint32_t bar_pfull = bars + 16u * S + 48u, bar_pempty = bars + 16u * S + 112u;   // 8 patch slots each (as conv_tc.cuh)
     float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + epi_bytes + 16u * S + 192u);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,6 +117,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
         if (p.mode == 2) { tma_prefetch_desc(&p.tmA[1]); tma_prefetch_desc(&p.tmA[2]); tma_prefetch_desc(&p.tmA[3]); }
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
         for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 2 * NEPI); }
+        for (int a = 0; a < 8; a++) { mbar_init(bar_pfull + 8u * a, 1); mbar_init(bar_pempty + 8u * a, 1); }
+        if (patch) tma_prefetch_desc(&p.tmA[1]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc_cg2(tmem_slot, TMEM_COLS);
@@ -124,19 +149,59 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     };
 
     if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
+        if (lane == 0 && patch) {
+            // A-patch reuse: per (tile, 64-channel block) ONE patch of 130 + 2*Wp rows (this CTA's 128 output rows shifted by
+            // -(Wp+1) .. +(Wp+1)) feeds all nine taps through row-shifted UMMA descriptors; only the weights ride the ring.  The
+            // pair kernel is bound by L2 -> shared-memory traffic on these layers (every tap re-fetched its A tile: 16 KB + 8 KB of
+            // weights per 256 tensor cycles per SM = 14 KB/clk chip-wide against ~6.3 KB/clk of TMA throughput): the patch cuts the
+            // A traffic to (130 + 2*Wp) / (9 * 128) of that.  Same K order (channel block outer, tap inner) as the per-tap loads.
+            const int ncb = p.kb_per_tap;
+            const int my_tiles = (p.num_tiles - cluster_id + nclusters - 1) / nclusters;
+            const int npatch = my_tiles > 0 ? my_tiles * ncb : 0;
+            const uint32_t PS = (uint32_t)p.patch_slots;
+            const uint32_t ptx = (uint32_t)p.patch_boxes * (uint32_t)p.patch_box_rows * 128u;
+            uint32_t it = 0, pit = 0;
+            auto issue_patch = [&](int j) {
+                const int tl = j / ncb, cb = j - tl * ncb;
+                const long long m0 = tile_m0(cluster_id + tl * nclusters);
+                const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
+                mbar_wait(bar_pempty + 8u * ps, pph ^ 1u);
+                if (rank == 0) mbar_expect_tx(bar_pfull + 8u * ps, 2u * ptx);
+                const uint32_t fb = (bar_pfull + 8u * ps) & kPeerBitMask;
+                const uint32_t dst = base + ps * (uint32_t)p.patch_bytes;
+                const int row0 = (int)m0 - 1 - p.Wp;
+                for (int b = 0; b < p.patch_boxes; b++)
+                    tma_load_2d_cg2(dst + (uint32_t)(b * p.patch_box_rows) * 128u, &p.tmA[1], fb, cb * BK, row0 + b * p.patch_box_rows);
+                pit++;
+            };
+            int issued = 0;
+            const int ahead = (int)PS > 2 ? (int)PS - 2 : 1;
+            for (int j = 0; j < npatch; j++) {
+                while (issued < npatch && issued <= j + ahead) issue_patch(issued++);
+                const int tl = j / ncb, cb = j - tl * ncb;
+                const int n0 = tile_n0(cluster_id + tl * nclusters);
+                for (int tap = 0; tap < 9; tap++, it++) {
+                    const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
+                    if (rank == 0) mbar_expect_tx(bar_full + 8u * s, 2u * (uint32_t)B_BYTES);
+                    tma_load_2d_cg2(bring + s * (uint32_t)B_BYTES, &p.tmW, (bar_full + 8u * s) & kPeerBitMask, (tap * ncb + cb) * BK,
+                                    n0 + (int)rank * (BN / 2));
+                }
+            }
+        } else if (!patch) {
+            // all 32 lanes run the loop (warp-uniform control flow, see elect_one); one elected lane issues
+            uint32_t s = 0, ph = 0;                                                   // ring stage and its phase (no per-stage division)
             for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters) {
                 const long long m0 = tile_m0(ct);
                 const int n0 = tile_n0(ct);
                 int bimg = 0, boh0 = 0, bow0 = 0;
                 if (p.mode == 2) box_tile(ct, bimg, boh0, bow0);
                 const uint32_t a_bytes = p.mode == 2 ? (uint32_t)(p.TH * p.TW * BK * 2) : (uint32_t)A_BYTES;
-                for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
-                    const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                for (int kb0 = 0; kb0 < p.num_kb; kb0 += G) {
                     mbar_wait(bar_empty + 8u * s, ph ^ 1u);
                     const uint32_t fb = (bar_full + 8u * s) & kPeerBitMask;          // the leader's barrier collects both CTAs' bytes
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
+                    if (elect_one()) {
                     if (rank == 0) mbar_expect_tx(bar_full + 8u * s, 2u * (uint32_t)gcount * (a_bytes + (uint32_t)B_BYTES));
                     for (int kk = 0; kk < gcount; kk++) {
                         const int kb = kb0 + kk;
@@ -159,19 +224,46 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                         }
                         tma_load_2d_cg2(sa + A_BYTES, &p.tmW, fb, (tap * p.kb_per_tap + cb) * BK, n0 + (int)rank * (BN / 2));
                     }
+                    }
+                    __syncwarp();
+                    if (++s == (uint32_t)S) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && rank == 0) {
-            uint32_t it = 0, ti = 0;
+        if (rank == 0) {                                     // all 32 lanes run the loop; the MMAs / commits are elect-predicated
+            uint32_t it = 0, ti = 0, pit = 0, ms = 0, mph = 0;
             for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters, ti++) {
                 const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
                 mbar_wait(bar_tempty + 8u * as, aph ^ 1u);                           // both CTAs' epilogues have drained this stage
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + as * (uint32_t)BN;
-                for (int kb0 = 0; kb0 < p.num_kb; kb0 += G, it++) {
-                    const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                if (patch) {
+                    const uint32_t PS = (uint32_t)p.patch_slots;
+                    for (int cb = 0; cb < p.kb_per_tap; cb++, pit++) {
+                        const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
+                        mbar_wait(bar_pfull + 8u * ps, pph);
+                        tc_fence_after();
+                        const uint32_t pa = base + ps * (uint32_t)p.patch_bytes;
+                        for (int tap = 0; tap < 9; tap++, it++) {
+                            const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                            mbar_wait(bar_full + 8u * s, ph);
+                            tc_fence_after();
+                            // patch row 0 is output row m0 shifted by -(Wp+1): tap (kh, kw) starts at row kh*Wp + kw
+                            const int roff = (tap / 3) * p.Wp + (tap % 3);
+                            const uint64_t da = make_smem_desc<SWZ>(pa + (uint32_t)roff * 128u);
+                            const uint64_t db = make_smem_desc<SWZ>(bring + s * (uint32_t)B_BYTES);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; k++)
+                                umma_f16_cg2_elect(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (cb | tap | k) ? 1u : 0u);
+                            umma_commit_cg2_elect(bar_empty + 8u * s);
+                        }
+                        umma_commit_cg2_elect(bar_pempty + 8u * ps);      // both CTAs' copies of this patch have been read
+                    }
+                } else
+                for (int kb0 = 0; kb0 < p.num_kb; kb0 += G) {
+                    const uint32_t s = ms, ph = mph;
+                    if (++ms == (uint32_t)S) { ms = 0; mph ^= 1u; }
                     mbar_wait(bar_full + 8u * s, ph);
                     tc_fence_after();
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
@@ -181,11 +273,11 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                         const uint64_t db = make_smem_desc<SWZ>(sa + A_BYTES);
 #pragma unroll
                         for (int k = 0; k < BK / 16; k++)
-                            umma_f16_cg2(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
+                            umma_f16_cg2_elect(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC, (kb0 | kk | k) ? 1u : 0u);
                     }
-                    umma_commit_cg2(bar_empty + 8u * s);
+                    umma_commit_cg2_elect(bar_empty + 8u * s);
                 }
-                umma_commit_cg2(bar_tfull + 8u * as);
+                umma_commit_cg2_elect(bar_tfull + 8u * as);
             }
         }
     } else {
@@ -360,7 +452,7 @@ inline int tc2_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 }
 
 // Plan for the CTA-pair kernel; returns the kernel kind (1 flat, 2 strided box) when the layer is eligible, 0 otherwise.
-inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn, int smem_budget_kb, int group, int nepi, int gw) {
+inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn, int smem_budget_kb, int group, int nepi, int gw, int patch = 0) {
     if (d.pairx && (d.cin != 32 || d.stride != 2 || d.k != 3 || !d.w16_pair || d.in_ld != 32 || d.in_choff != 0)) return 0;
     const int cin = d.pairx ? 64 : d.cin;
     const int ntaps = d.pairx ? 6 : d.k * d.k;
@@ -438,20 +530,40 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
                 if (!encode_map(&p.tmA[ph * 2 + pw], b, 4, dims, str, box4, 128, err)) return -1;
             }
     }
-    if (group < 1) group = 1;
+    if (patch || group < 1) group = 1;
     if (group > p.num_kb) group = p.num_kb;
     p.group = group;
     const size_t epi_bytes = box ? 0 : epi_slab_bytes(nepi, gw);
-    const size_t stage_bytes = ((size_t)128 * 64 * 2 + (size_t)(bn / 2) * 64 * 2) * group;
+    size_t stage_bytes = ((size_t)128 * 64 * 2 + (size_t)(bn / 2) * 64 * 2) * group;
     const size_t fixed = 1024 + epi_bytes + 16 * 8 + 192 + 4 * (size_t)d.cout_pad;
     const size_t budget = (size_t)smem_budget_kb * 1024;
-    int S = budget > fixed ? (int)((budget - fixed) / stage_bytes) : 0;
-    if (S > 8) S = 8;
-    if (S < 2) return 0;
+    size_t patch_total = 0;
+    int S;
+    if (patch) {
+        // A-patch reuse (mode 3): 3x3 stride 1 only; one patch = 130 + 2*Wp rows of 128 B in 32-row TMA boxes; the ring holds B only
+        if (box || d.k != 3 || patch != 1) return 0;
+        p.mode = 3; p.patch_taps = 9; p.patch_box_rows = 32; p.patch_boxes = (130 + 2 * in_Wp + 31) / 32;
+        p.patch_bytes = ((p.patch_boxes * 32 * 128 + 1023) / 1024) * 1024;
+        cuuint64_t dims[2] = {(cuuint64_t)d.cin, (cuuint64_t)p.rows_alloc};
+        cuuint64_t str[1] = {(cuuint64_t)d.in_ld * 2};
+        cuuint32_t box2[2] = {64, 32};
+        if (!encode_map(&p.tmA[1], in_base, 2, dims, str, box2, 128, err)) return -1;
+        stage_bytes = (size_t)(bn / 2) * 64 * 2;
+        S = 6;                                                         // B stages: a half B tile is small and re-fetched per tap
+        const size_t bpart = (size_t)S * stage_bytes;
+        if (budget < fixed + bpart + 2 * (size_t)p.patch_bytes) return 0;
+        int PS = (int)((budget - fixed - bpart) / (size_t)p.patch_bytes);
+        p.patch_slots = PS > 4 ? 4 : PS;
+        patch_total = (size_t)p.patch_slots * (size_t)p.patch_bytes;
+    } else {
+        S = budget > fixed ? (int)((budget - fixed) / stage_bytes) : 0;
+        if (S > 8) S = 8;
+        if (S < 2) return 0;
+    }
     P.stages = S; p.stages = S;
     p.n_tiles = d.cout_pad / bn;
     p.bias_n = d.cout_pad;
-    P.smem = 1024 + S * stage_bytes + epi_bytes + 16 * S + 192 + 4 * (size_t)p.bias_n;
+    P.smem = 1024 + patch_total + S * stage_bytes + epi_bytes + 16 * S + 192 + 4 * (size_t)p.bias_n;
     if (P.smem > 225 * 1024) return 0;
     *pl = P;
     return P.kind;

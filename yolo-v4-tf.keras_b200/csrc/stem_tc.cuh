@@ -4,8 +4,9 @@
 //
 // One tile = 16 x 8 conv-1 outputs of one image = 128 rows of the conv-1 GEMM.  It needs the 33 x 17 conv-0 outputs
 // (2*oh0-1 .., 2*ow0-1 ..), computed here (9.6 % recompute on the tile borders) and kept in shared memory:
-//   G   every thread builds conv-0 im2col rows (27 image values -> 32 fp16 = one 64 B K-major row, as conv0_tc.cuh) for the
-//       561 patch pixels, ordered PLANE-MAJOR: the patch is stored as its four (row parity, column parity) planes, 17x9, 17x8,
+//   G0  the 35 x 19 image pixels under the patch are staged in shared memory as fp16 (c0, c1, c2, 0), zero outside the image;
+//   G   every thread builds conv-0 im2col rows (27 halfs + 5 zeros = one 64 B K-major row, K order as conv0_tc.cuh: 9 LDS.64 +
+//       8 PRMT per row instead of 27 predicated global loads) for the 561 patch pixels, ordered PLANE-MAJOR: the patch is stored as its four (row parity, column parity) planes, 17x9, 17x8,
 //       16x9, 16x8 pixels, because tap (kh, kw) of the stride-2 conv reads plane (kh&1, kw&1) at offset (kh>>1, kw>>1):
 //       8 consecutive outputs of a tile row are 8 CONSECUTIVE plane pixels = one 8-row core group of a K-major UMMA operand,
 //       and the 16 tile rows are 16 groups one plane pitch apart (the descriptor's stride-byte-offset);
@@ -41,7 +42,9 @@ constexpr uint32_t kStemSlab = kStemRowsPad * 64;   // [128][128 B] conv-1 outpu
 constexpr uint32_t kStemB1 = kStemSlab + 128 * 128; // 9 x [64][64 B]  conv-1 weights, SWIZZLE_64B
 constexpr uint32_t kStemB0 = kStemB1 + 9 * 64 * 64; // [32][64 B]      conv-0 weights, SWIZZLE_64B
 constexpr uint32_t kStemBars = kStemB0 + 32 * 64;   // 3 mbarriers + tmem slot, then the biases
-constexpr uint32_t kStemSmem = kStemBars + 64 + 96 * 4 + 1024;   // + alignment slack
+constexpr uint32_t kStemPatch = kStemBars + 64 + 96 * 4;         // [35][19] image pixels as 4 x fp16 (c0, c1, c2, 0), zero outside the image
+constexpr uint32_t kStemPatchBytes = 35 * 19 * 8;               // two of them: this tile's and the next one's
+constexpr uint32_t kStemSmem = kStemPatch + 2 * kStemPatchBytes + 1024;  // + alignment slack
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
@@ -62,6 +65,35 @@ __device__ __forceinline__ void stem_row_to_patch(int m, int& i, int& j) {
     const int prow = r / pw_;
     i = 2 * prow + ph;
     j = 2 * (r - prow * pw_) + pc;
+}
+
+// image pixels idx = tid, tid + 256, tid + 512 of the 35 x 19 patch of `tile` -> registers (zero outside the image)
+__device__ __forceinline__ void stem_patch_load(const StemParams& p, int tile, int tid, float (&v)[3][3]) {
+    const int twi = tile % p.tiles_w;
+    const int t2 = tile / p.tiles_w;
+    const int thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
+    const int y0 = 32 * thi - 1, x0 = 16 * twi - 1;
+    const float* img = p.img + (long long)n * p.S * p.S * 3;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int idx = tid + k * kStemThreads;
+        const int r = idx / 19, c = idx - r * 19;
+        const int iy = y0 - 1 + r, ix = x0 - 1 + c;
+        const bool ok = idx < 35 * 19 && iy >= 0 && iy < p.S && ix >= 0 && ix < p.S;
+        const float* px = img + ((long long)(ok ? iy : 0) * p.S + (ok ? ix : 0)) * 3;
+        v[k][0] = ok ? __ldg(px) : 0.f; v[k][1] = ok ? __ldg(px + 1) : 0.f; v[k][2] = ok ? __ldg(px + 2) : 0.f;
+    }
+}
+__device__ __forceinline__ void stem_patch_store(unsigned char* buf, int tid, const float (&v)[3][3]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int idx = tid + k * kStemThreads;
+        if (idx < 35 * 19) {
+            __half2 h01 = __floats2half2_rn(v[k][0], v[k][1]);
+            __half2 h2z = __floats2half2_rn(v[k][2], 0.f);
+            reinterpret_cast<uint2*>(buf)[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&h01), *reinterpret_cast<uint32_t*>(&h2z));
+        }
+    }
 }
 
 __global__ void __launch_bounds__(kStemThreads, 2) stem_tc_kernel(const __grid_constant__ StemParams p) {
@@ -102,63 +134,66 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_tc_kernel(const __grid_c
 
     const int S = p.S;
     const int q = warp & 3, set = warp >> 2;               // TMEM lane quarter of this warp; which half of the work it takes
-    uint32_t phase = 0;
+    uint32_t phase = 0, pbuf = 0;
     bool w_ready = false;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    if ((int)blockIdx.x < p.num_tiles) {                   // prologue: the first tile's patch
+        float pre0[3][3];
+        stem_patch_load(p, (int)blockIdx.x, tid, pre0);
+        stem_patch_store(sm + kStemPatch, tid, pre0);
+    }
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, pbuf ^= 1u) {
         const int twi = tile % p.tiles_w;
         const int t2 = tile / p.tiles_w;
         const int thi = t2 % p.tiles_h, n = t2 / p.tiles_h;
         const int oh0 = thi * 16, ow0 = twi * 8;
         const int y0 = 2 * oh0 - 1, x0 = 2 * ow0 - 1;     // conv-0 pixel of patch position (0, 0)
-        const float* img = p.img + (long long)n * S * S * 3;
 
-        // ---- G: conv-0 im2col rows, plane-major (k = (kh*3 + kw)*3 + c, as conv0_tc_kernel)
+        // ---- G0 (software-pipelined): the 35 x 19 image pixels under the NEXT tile's patch are requested here (global loads into
+        // registers, nothing waits on them) and written to the other patch buffer at the end of this tile, fp16 (c0, c1, c2, 0),
+        // zero outside the image ('same'); this tile's patch was staged during the previous one (prologue for the first).
+        const uint2* spatch = reinterpret_cast<const uint2*>(sm + kStemPatch + (pbuf ? kStemPatchBytes : 0u));
+        float pre[3][3];
+        const int ntile = tile + (int)gridDim.x;
+        if (ntile < p.num_tiles) stem_patch_load(p, ntile, tid, pre);
+        // ---- G: conv-0 im2col rows, plane-major: K index (kh*3 + kw)*3 + c (as conv0_tc_kernel), 27 halfs packed from 9 pixels
         for (int m = tid; m < kStemRows; m += kStemThreads) {
             int i, j;
             stem_row_to_patch(m, i, j);
-            const int y = y0 + i, x = x0 + j;
-            float v[32];
+            uint32_t a[9], b[9];
 #pragma unroll
-            for (int k = 27; k < 32; k++) v[k] = 0.f;
-#pragma unroll
-            for (int kh = 0; kh < 3; kh++) {
-                const int yy = y + kh - 1;
-                const bool yok = yy >= 0 && yy < S && y >= 0 && x >= 0;
-                const float* rp = img + (long long)(yok ? yy : 0) * S * 3;
+            for (int kh = 0; kh < 3; kh++)
 #pragma unroll
                 for (int kw = 0; kw < 3; kw++) {
-                    const int xx = x + kw - 1;
-                    const bool ok = yok && xx >= 0 && xx < S;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) v[(kh * 3 + kw) * 3 + c] = ok ? __ldg(rp + xx * 3 + c) : 0.f;
+                    const uint2 v = spatch[(i + kh) * 19 + j + kw];
+                    a[kh * 3 + kw] = v.x; b[kh * 3 + kw] = v.y;
                 }
-            }
+            uint32_t w[16];
 #pragma unroll
-            for (int c4 = 0; c4 < 4; c4++) {
-                __half2 h0 = __floats2half2_rn(v[8 * c4 + 0], v[8 * c4 + 1]);
-                __half2 h1 = __floats2half2_rn(v[8 * c4 + 2], v[8 * c4 + 3]);
-                __half2 h2 = __floats2half2_rn(v[8 * c4 + 4], v[8 * c4 + 5]);
-                __half2 h3 = __floats2half2_rn(v[8 * c4 + 6], v[8 * c4 + 7]);
-                uint4 u;
-                u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(sm + kStemA + m * 64 + ((c4 ^ ((m >> 1) & 3)) << 4)) = u;
+            for (int t = 0; t < 4; t++) {
+                w[3 * t] = a[2 * t];
+                w[3 * t + 1] = __byte_perm(b[2 * t], a[2 * t + 1], 0x5410);        // (c2 of pixel 2t, c0 of pixel 2t+1)
+                w[3 * t + 2] = __byte_perm(a[2 * t + 1], b[2 * t + 1], 0x5432);    // (c1, c2 of pixel 2t+1)
             }
+            w[12] = a[8]; w[13] = b[8]; w[14] = 0u; w[15] = 0u;                     // b[8] = (c2, 0): k = 26, 27
+#pragma unroll
+            for (int c4 = 0; c4 < 4; c4++)
+                *reinterpret_cast<uint4*>(sm + kStemA + m * 64 + ((c4 ^ ((m >> 1) & 3)) << 4)) = make_uint4(w[4 * c4], w[4 * c4 + 1], w[4 * c4 + 2], w[4 * c4 + 3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
         __syncthreads();
         // ---- M0: conv 0, five 128-row tiles
-        if (tid == 0) {
+        if (warp == 0) {                                   // whole warp, elect-predicated issue (conv_tc.cuh elect_one)
             tc_fence_after();
             const uint64_t db = make_smem_desc<64>(b0_addr);
 #pragma unroll
             for (int t = 0; t < 5; t++) {
                 const uint64_t da = make_smem_desc<64>(a_addr + (uint32_t)t * 8192u);
-                umma_f16(tmem_base + (uint32_t)(32 * t), da, db, IDESC0, 0u);
-                umma_f16(tmem_base + (uint32_t)(32 * t), da + 2ull, db + 2ull, IDESC0, 1u);
+                umma_f16_elect(tmem_base + (uint32_t)(32 * t), da, db, IDESC0, 0u);
+                umma_f16_elect(tmem_base + (uint32_t)(32 * t), da + 2ull, db + 2ull, IDESC0, 1u);
             }
-            umma_commit(bar0);
+            umma_commit_elect(bar0);
         }
         mbar_wait(bar0, phase);
         tc_fence_after();
@@ -193,7 +228,7 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_tc_kernel(const __grid_c
         tc_fence_before();
         __syncthreads();
         // ---- M1: conv 1, tap outer / channel inner; A = plane (kh&1, kw&1) shifted by (kh>>1, kw>>1), 16 groups one plane pitch apart
-        if (tid == 0) {
+        if (warp == 0) {
             if (!w_ready) { mbar_wait(bar_w, 0u); w_ready = true; }
             tc_fence_after();
 #pragma unroll
@@ -205,11 +240,12 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_tc_kernel(const __grid_c
                 const uint32_t row0 = (uint32_t)(pbase + (kh >> 1) * pitch + (kw >> 1));
                 const uint64_t da = make_smem_desc_sw64_sbo(a_addr + row0 * 64u, (uint32_t)pitch * 64u);
                 const uint64_t db = make_smem_desc<64>(b1_addr + (uint32_t)tap * 4096u);
-                umma_f16(tmem_base + 192u, da, db, IDESC1, tap ? 1u : 0u);
-                umma_f16(tmem_base + 192u, da + 2ull, db + 2ull, IDESC1, 1u);
+                umma_f16_elect(tmem_base + 192u, da, db, IDESC1, tap ? 1u : 0u);
+                umma_f16_elect(tmem_base + 192u, da + 2ull, db + 2ull, IDESC1, 1u);
             }
-            umma_commit(bar1);
-            bulk_wait_read<0>();                           // the previous tile's TMA store has finished reading the slab
+            umma_commit_elect(bar1);
+            if (lane == 0) bulk_wait_read<0>();            // the previous tile's TMA store (issued by thread 0) has finished reading the slab
+            __syncwarp();
         }
         mbar_wait(bar1, phase);
         phase ^= 1u;
@@ -237,9 +273,10 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_tc_kernel(const __grid_c
                 *reinterpret_cast<uint4*>(sm + kStemSlab + m * 128 + ((chunk ^ (m & 7)) << 4)) = o;
             }
         }
+        if (ntile < p.num_tiles) stem_patch_store(sm + kStemPatch + (pbuf ? 0u : kStemPatchBytes), tid, pre);   // the next tile's patch
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         tc_fence_before();
-        __syncthreads();                                   // slab complete; TMEM and the A region are free for the next tile
+        __syncthreads();                                   // slab + next patch complete; TMEM and the A region are free for the next tile
         if (tid == 0) { tma_store_4d(&p.tmOut, slab_addr, 0, ow0 + 1, oh0 + 1, n); bulk_commit(); }
     }
     if (tid == 0) bulk_wait_all();

@@ -802,6 +802,10 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                     for (int g : {1, 2, 3})
                         for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}})
                             cands.push_back({bn, 224, 0, g, 1, ep.first, 0, ep.second, 1});
+            if (allow_cta2 && !(getenv("Y4_PATCH2") && getenv("Y4_PATCH2")[0] == '0'))   // CTA pair + A-patch reuse (3x3 stride 1): cuts the L2 -> smem traffic
+                for (int bn : {64, 128, 256})
+                    for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}})
+                        cands.push_back({bn, 224, 1, 1, 1, ep.first, 0, ep.second, 1});
             for (int bres = 0; bres <= (allow_bres ? 1 : 0); bres++)            // lean 4-warp epilogue, four CTAs per SM (64-wide tiles)
                 for (int gw : {32, 64})
                     for (int kb : {56, 75}) cands.push_back({64, kb, 0, 1, 1, 4, bres, gw, 0, 1});
@@ -876,7 +880,7 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                     TcConvDesc dd = c.desc;
                     dd.pairx = cd.pairx;
                     if (cd.pairx && !dd.w16_pair) continue;
-                    if (cd.cta2) { if (tc_plan2(dd, &trial[li], &er2, cd.bn, cd.kb, cd.group, cd.nepi, cd.gw) != c.kind) continue; }
+                    if (cd.cta2) { if (tc_plan2(dd, &trial[li], &er2, cd.bn, cd.kb, cd.group, cd.nepi, cd.gw, cd.patch) != c.kind) continue; }
                     else if (tc_plan(dd, &trial[li], &er2, cd.bn, cd.kb, cd.patch, cd.group, cd.epi, cd.nepi, cd.bres, cd.gw, cd.lean) != c.kind) continue;
                     has[li] = 1; any = true;
                 }
@@ -1294,7 +1298,7 @@ int y4_describe_layer(const y4_engine* e, int32_t idx, y4_layer_info* info) {
     info->flops = 2ll * c.N_OH * c.N_OH * c.cout * c.K;
     snprintf(info->out_name, sizeof(info->out_name), "%s", c.out_name.c_str());
     const bool tc = c.kind == 1 || c.kind == 2;
-    info->tc_mode = tc ? (c.tc.cta2 ? 4 : c.tc.p.mode) : 0; info->tc_epilogue = tc && c.tc.p.epi ? c.tc.p.epi_gw : 0; info->tc_stages = tc ? c.tc.stages : 0;
+    info->tc_mode = tc ? (c.tc.cta2 ? (c.tc.p.mode == 3 ? 5 : 4) : c.tc.p.mode) : 0; info->tc_epilogue = tc && c.tc.p.epi ? c.tc.p.epi_gw : 0; info->tc_stages = tc ? c.tc.stages : 0;
     info->tc_group = tc ? c.tc.p.group : 0; info->tc_ctas_per_sm = tc ? c.tc.ctas_per_sm : 0; info->tc_bk = tc ? c.tc.bk : 0;
     info->tc_epi_warps = tc ? (c.tc.lean ? 44 : c.tc.nepi) : 0; info->tc_resident_w = tc ? c.tc.p.bres : 0;
     return Y4_OK;
