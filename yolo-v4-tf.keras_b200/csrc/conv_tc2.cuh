@@ -149,44 +149,49 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     };
 
     if (warp == 0) {
-        if (lane == 0 && patch) {
+        if (patch) {
             // A-patch reuse: per (tile, 64-channel block) ONE patch of 130 + 2*Wp rows (this CTA's 128 output rows shifted by
-            // -(Wp+1) .. +(Wp+1)) feeds all nine taps through row-shifted UMMA descriptors; only the weights ride the ring.  The
-            // pair kernel is bound by L2 -> shared-memory traffic on these layers (every tap re-fetched its A tile: 16 KB + 8 KB of
-            // weights per 256 tensor cycles per SM = 14 KB/clk chip-wide against ~6.3 KB/clk of TMA throughput): the patch cuts the
-            // A traffic to (130 + 2*Wp) / (9 * 128) of that.  Same K order (channel block outer, tap inner) as the per-tap loads.
+            // -(Wp+1) .. +(Wp+1)) feeds all nine taps through row-shifted UMMA descriptors; only the weights ride the ring: the A
+            // traffic from L2 drops to (130 + 2*Wp) / (9 * 128) of the per-tap loads.  Same K order (channel block outer, tap inner).
+            // All 32 lanes run the loop (warp-uniform, see elect_one); patches are issued up to PS - 2 ahead of the weight loads.
             const int ncb = p.kb_per_tap;
             const int my_tiles = (p.num_tiles - cluster_id + nclusters - 1) / nclusters;
             const int npatch = my_tiles > 0 ? my_tiles * ncb : 0;
             const uint32_t PS = (uint32_t)p.patch_slots;
             const uint32_t ptx = (uint32_t)p.patch_boxes * (uint32_t)p.patch_box_rows * 128u;
-            uint32_t it = 0, pit = 0;
-            auto issue_patch = [&](int j) {
-                const int tl = j / ncb, cb = j - tl * ncb;
-                const long long m0 = tile_m0(cluster_id + tl * nclusters);
-                const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
-                mbar_wait(bar_pempty + 8u * ps, pph ^ 1u);
-                if (rank == 0) mbar_expect_tx(bar_pfull + 8u * ps, 2u * ptx);
-                const uint32_t fb = (bar_pfull + 8u * ps) & kPeerBitMask;
-                const uint32_t dst = base + ps * (uint32_t)p.patch_bytes;
-                const int row0 = (int)m0 - 1 - p.Wp;
-                for (int b = 0; b < p.patch_boxes; b++)
-                    tma_load_2d_cg2(dst + (uint32_t)(b * p.patch_box_rows) * 128u, &p.tmA[1], fb, cb * BK, row0 + b * p.patch_box_rows);
-                pit++;
-            };
-            int issued = 0;
+            uint32_t bs = 0, bph = 0, ps = 0, pph = 0;       // weight-ring stage / phase, patch slot / phase
+            int issued = 0, itl = 0, icb = 0;                // next patch to issue: its tile (local index) and channel block
             const int ahead = (int)PS > 2 ? (int)PS - 2 : 1;
+            int tl = 0, cb = 0;
             for (int j = 0; j < npatch; j++) {
-                while (issued < npatch && issued <= j + ahead) issue_patch(issued++);
-                const int tl = j / ncb, cb = j - tl * ncb;
-                const int n0 = tile_n0(cluster_id + tl * nclusters);
-                for (int tap = 0; tap < 9; tap++, it++) {
-                    const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
-                    mbar_wait(bar_empty + 8u * s, ph ^ 1u);
-                    if (rank == 0) mbar_expect_tx(bar_full + 8u * s, 2u * (uint32_t)B_BYTES);
-                    tma_load_2d_cg2(bring + s * (uint32_t)B_BYTES, &p.tmW, (bar_full + 8u * s) & kPeerBitMask, (tap * ncb + cb) * BK,
-                                    n0 + (int)rank * (BN / 2));
+                while (issued < npatch && issued <= j + ahead) {
+                    const long long m0 = tile_m0(cluster_id + itl * nclusters);
+                    mbar_wait(bar_pempty + 8u * ps, pph ^ 1u);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(bar_pfull + 8u * ps, 2u * ptx);
+                        const uint32_t fb = (bar_pfull + 8u * ps) & kPeerBitMask;
+                        const uint32_t dst = base + ps * (uint32_t)p.patch_bytes;
+                        const int row0 = (int)m0 - 1 - p.Wp;
+                        for (int b = 0; b < p.patch_boxes; b++)
+                            tma_load_2d_cg2(dst + (uint32_t)(b * p.patch_box_rows) * 128u, &p.tmA[1], fb, icb * BK, row0 + b * p.patch_box_rows);
+                    }
+                    __syncwarp();
+                    if (++ps == PS) { ps = 0; pph ^= 1u; }
+                    if (++icb == ncb) { icb = 0; itl++; }
+                    issued++;
                 }
+                const int n0 = tile_n0(cluster_id + tl * nclusters);
+                for (int tap = 0; tap < 9; tap++) {
+                    mbar_wait(bar_empty + 8u * bs, bph ^ 1u);
+                    if (elect_one()) {
+                        if (rank == 0) mbar_expect_tx(bar_full + 8u * bs, 2u * (uint32_t)B_BYTES);
+                        tma_load_2d_cg2(bring + bs * (uint32_t)B_BYTES, &p.tmW, (bar_full + 8u * bs) & kPeerBitMask, (tap * ncb + cb) * BK,
+                                        n0 + (int)rank * (BN / 2));
+                    }
+                    __syncwarp();
+                    if (++bs == (uint32_t)S) { bs = 0; bph ^= 1u; }
+                }
+                if (++cb == ncb) { cb = 0; tl++; }
             }
         } else if (!patch) {
             // all 32 lanes run the loop (warp-uniform control flow, see elect_one); one elected lane issues
@@ -232,7 +237,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
         }
     } else if (warp == 1) {
         if (rank == 0) {                                     // all 32 lanes run the loop; the MMAs / commits are elect-predicated
-            uint32_t it = 0, ti = 0, pit = 0, ms = 0, mph = 0;
+            uint32_t ti = 0, ms = 0, mph = 0, mps = 0, mpph = 0;
             for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters, ti++) {
                 const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
                 mbar_wait(bar_tempty + 8u * as, aph ^ 1u);                           // both CTAs' epilogues have drained this stage
@@ -240,13 +245,15 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                 const uint32_t tacc = tmem_base + as * (uint32_t)BN;
                 if (patch) {
                     const uint32_t PS = (uint32_t)p.patch_slots;
-                    for (int cb = 0; cb < p.kb_per_tap; cb++, pit++) {
-                        const uint32_t ps = pit % PS, pph = (pit / PS) & 1u;
+                    for (int cb = 0; cb < p.kb_per_tap; cb++) {
+                        const uint32_t ps = mps, pph = mpph;
+                        if (++mps == PS) { mps = 0; mpph ^= 1u; }
                         mbar_wait(bar_pfull + 8u * ps, pph);
                         tc_fence_after();
                         const uint32_t pa = base + ps * (uint32_t)p.patch_bytes;
-                        for (int tap = 0; tap < 9; tap++, it++) {
-                            const uint32_t s = it % (uint32_t)S, ph = (it / (uint32_t)S) & 1u;
+                        for (int tap = 0; tap < 9; tap++) {
+                            const uint32_t s = ms, ph = mph;
+                            if (++ms == (uint32_t)S) { ms = 0; mph ^= 1u; }
                             mbar_wait(bar_full + 8u * s, ph);
                             tc_fence_after();
                             // patch row 0 is output row m0 shifted by -(Wp+1): tap (kh, kw) starts at row kh*Wp + kw
