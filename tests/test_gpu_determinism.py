@@ -161,3 +161,33 @@ def test_stem_fusion_is_bit_identical(weights, size, batch):
     assert np.array_equal(c1a, c1b), float(np.abs(c1a - c1b).max())
     for a, b in zip(res['stem'][0], res['separate'][0]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize('size,batch', [(160, 2), (608, 1)])
+def test_chain_fusion_is_bit_identical(weights, size, batch):
+    """A 1x1 conv that reads exactly what the previous launch wrote (residual_block's first conv on r_k, custom_layers.py:38;
+    the first residual after csp_block's main conv) runs inside that launch, on the output tile in shared memory (CTA-pair
+    kernel, second MMA into the drained TMEM stage).  Every tensor must equal the separate launches (Y4_CHAIN=0) bit for bit."""
+    import y4b200
+    import y4_oracle as O
+    W, blob = weights
+    imgs = O.synth_images(0, 0, batch, size)
+    names = ['c4', 'r1', 'c11', 'r2', 'c13', 'r3', 'c15', 'c20', 'r4', 'c22', 'r11', 'c36', 'cat3', 'r12', 'c43', 'c58']
+    res = {}
+    for tag, env in (('chain', '1'), ('separate', None)):          # opt-in: measured slower than the separate launches (y4_engine.cu)
+        os.environ.pop('Y4_CHAIN', None)
+        if env:
+            os.environ['Y4_CHAIN'] = env
+        try:
+            eng = y4b200.Engine(img_size=size, max_batch=batch, precision=y4b200.PREC_FP16)
+        finally:
+            os.environ.pop('Y4_CHAIN', None)
+        eng.load_darknet_bytes(blob)
+        heads = eng.forward_heads(imgs)
+        res[tag] = (heads + [eng.get_tensor(n, batch) for n in names], eng.steps())
+        eng.close()
+    chained = [s['out_name'] for s in res['chain'][1] if '>' in s['out_name']]
+    assert len(chained) >= 10, chained
+    assert len(res['chain'][1]) == len(res['separate'][1]) - len(chained)
+    for n, a, b in zip(['hs', 'hm', 'hl'] + names, res['chain'][0], res['separate'][0]):
+        assert np.array_equal(a, b), (n, float(np.abs(a - b).max()))

@@ -42,6 +42,11 @@ struct TcConvDesc {
     // sibling fusion: two convs that read the same input (csp_block's route / main 1x1, custom_layers.py:59-60) run as ONE GEMM
     // with cout = 2C; output columns [0, split_col) go to `out`, columns [split_col, cout) to `out2` (slab epilogue only)
     void* out2; int out2_ld, out2_choff, split_col;
+    // chain fusion (CTA-pair kernel only): the 1x1 conv Q that follows this conv (residual_block's first conv on the block input,
+    // custom_layers.py:38; csp_block's first residual after the main 1x1) runs on the output tile while it is still in shared
+    // memory: Q's input = this conv's output columns [q_col0, q_col0 + q_cin)
+    int q_on; const __half* q_w16; const float* q_bias; int q_cin, q_cout, q_cout_pad, q_act, q_col0;
+    void* q_out; int q_out_ld, q_out_choff;
     // pixel-pair view for a 3x3 stride-2 conv with cin = 32 (conv 1): two neighbouring pixels = 64 contiguous channels, so the taps
     // (kh, kw=0|1) are ONE 128 B-row box and (kh, kw=2|zero) another: 6 taps of 64 instead of 9 of 32 (w16_pair: [cout_pad][6*64])
     int pairx; const __half* w16_pair;
@@ -56,7 +61,11 @@ struct TcParams {
     CUtensorMap tmW_lo;
     CUtensorMap tmOut;           // epi = 1: output slice as [rows][cout] fp16, box {32 channels, 32 rows}, SWIZZLE_64B (TMA store of the slabs)
     CUtensorMap tmOut2;          // sibling fusion: second destination, for output columns >= split_col
+    CUtensorMap tmW2;            // chain fusion: Q's weights [q_n][64 * q_kb] fp16, box {64, q_n / 2}, SWIZZLE_128B
+    CUtensorMap tmOutQ;          // chain fusion: Q's output slice, box {gw, 32}
     int split_col;               // 0: single destination
+    int q_on, q_kb, q_n, q_col0, q_cout_store, q_act;   // chain fusion: K blocks of Q, N of the second MMA (cout_pad of Q), first input column, columns stored
+    const float* q_bias;
     const float* bias;
     const float* wscale;         // per-cout 1/scale of the (power-of-two scaled) split weights, nullptr -> 1
     void* out;
@@ -120,6 +129,16 @@ __device__ __forceinline__ uint32_t mbar_try(uint32_t bar, uint32_t parity) {
         "{\n\t"
         ".reg .pred P1;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {       // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, P1;\n\t"
         "}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok;
@@ -506,10 +525,11 @@ __device__ __forceinline__ void res_prefetch(const TcParams& p, uint32_t slab, l
 
 // 32 accumulator columns of this thread's row -> activation (-> + skip chunk from the slab) -> fp16 -> slab chunks 4h..4h+3
 __device__ __forceinline__ void epi_group(const TcParams& p, const uint32_t (&v)[32], const float* sb, uint32_t slab, int lane, int h,
-                                          bool interior, bool has_res, bool gw64) {
+                                          bool interior, bool has_res, bool gw64, int act_sel = -1) {
     float f[32];
-    if (p.act == 2) act32_fast<2>(v, sb, f);
-    else if (p.act == 1) act32_fast<1>(v, sb, f);
+    const int act = act_sel < 0 ? p.act : act_sel;          // chain fusion: the second conv's activation
+    if (act == 2) act32_fast<2>(v, sb, f);
+    else if (act == 1) act32_fast<1>(v, sb, f);
     else act32_fast<0>(v, sb, f);
     if (p.out_f32) {                                        // fp32 heads: 32 columns = one 128 B slab row (SWIZZLE_128B), no skip tensor
 #pragma unroll
@@ -1162,7 +1182,7 @@ inline int tc_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
 // returns kernel kind (0 = not eligible -> CUDA-core kernel, 1 = flat GEMM, 2 = strided box), <0 on error
 inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn_req = 0, int smem_budget_kb = 99, int patch = 0, int group = 1,
                    int epi = 0, int nepi = 4, int bres = 0, int gw = 32, int lean = 0) {
-    if (d.raw_in) return 0;                                   // conv 0 (cin = 3): CUDA-core kernel
+    if (d.raw_in || d.q_on) return 0;                         // conv 0 (cin = 3): CUDA-core kernel; chain fusion: CTA-pair kernel only
     if (d.pairx && (d.cin != 32 || d.stride != 2 || d.k != 3 || d.split || !d.w16_pair || d.in_ld != 32 || d.in_choff != 0)) return 0;
     const int cin = d.pairx ? 64 : d.cin;                     // pixel-pair view: 64 channels per (pair) pixel
     const int ntaps = d.pairx ? 6 : d.k * d.k;

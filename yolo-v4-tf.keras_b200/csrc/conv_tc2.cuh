@@ -98,12 +98,20 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                                       : (uint32_t)(S * G) * (uint32_t)STAGE_BYTES;
     const uint32_t bring = base + (uint32_t)(p.patch_slots * p.patch_bytes);   // mode 3: first B stage
     const uint32_t epi_bytes = p.epi ? epi_slab_bytes(NEPI, p.epi_gw) : 0u;
-    const uint32_t slabs = base + ring_bytes;
+    // chain fusion: A2 = this CTA's 128 output rows x 64*q_kb channels as q_kb K-major SWIZZLE_128B blocks (the second MMA's A
+    // operand, written by the epilogue warps); W2 = this CTA's half of Q's weights, resident
+    const uint32_t a2_bytes = p.q_on ? (uint32_t)p.q_kb * 16384u : 0u;
+    const uint32_t w2_blk = (uint32_t)(p.q_n / 2) * 128u;
+    const uint32_t w2_bytes = p.q_on ? (uint32_t)p.q_kb * w2_blk : 0u;
+    const uint32_t a2 = base + ring_bytes, w2 = a2 + a2_bytes;
+    const uint32_t slabs = w2 + ((w2_bytes + 1023u) & ~1023u);
     const uint32_t bars = slabs + epi_bytes;
     const uint32_t bar_full = bars, bar_empty = bars + 8u * S, bar_tfull = bars + 16u * S, bar_tempty = bars + 16u * S + 16u;
     const uint32_t tmem_slot = bars + 16u * S + 32u;
     const uint32_t bar_pfull = bars + 16u * S + 48u, bar_pempty = bars + 16u * S + 112u;   // 8 patch slots each (as conv_tc.cuh)
-    float* sbias = reinterpret_cast<float*>(tc_smem + (base - raw) + ring_bytes + epi_bytes + 16u * S + 192u);
+    const uint32_t bar_a2full = bars + 16u * S + 176u, bar_t2full = bars + 16u * S + 184u, bar_w2 = bars + 16u * S + 192u;
+    float* sbias = reinterpret_cast<float*>(tc_smem + (slabs - raw) + epi_bytes + 16u * S + 224u);
+    float* sbias2 = sbias + p.bias_n;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -118,12 +126,15 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8u * s, 1); mbar_init(bar_empty + 8u * s, 1); }
         for (int a = 0; a < 2; a++) { mbar_init(bar_tfull + 8u * a, 1); mbar_init(bar_tempty + 8u * a, 2 * NEPI); }
         for (int a = 0; a < 8; a++) { mbar_init(bar_pfull + 8u * a, 1); mbar_init(bar_pempty + 8u * a, 1); }
+        mbar_init(bar_a2full, 2 * NEPI); mbar_init(bar_t2full, 1); mbar_init(bar_w2, 1);
+        if (p.q_on) { tma_prefetch_desc(&p.tmW2); tma_prefetch_desc(&p.tmOutQ); }
         if (patch) tma_prefetch_desc(&p.tmA[1]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc_cg2(tmem_slot, TMEM_COLS);
     const float bmul = p.act == 2 ? 1.4426950408889634f : 1.0f;          // mish layers keep b * log2(e) (act_fast)
     if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 32 * NEPI) sbias[i] = p.bias[i] * bmul;
+    if (warp >= 2 && p.q_on) for (int i = threadIdx.x - 64; i < p.q_n; i += 32 * NEPI) sbias2[i] = p.q_bias[i] * (p.q_act == 2 ? 1.4426950408889634f : 1.0f);
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();                                     // the peer's barriers exist before anything is signalled across the pair
@@ -149,6 +160,14 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     };
 
     if (warp == 0) {
+        if (p.q_on) {
+            if (elect_one()) {
+                if (rank == 0) mbar_expect_tx(bar_w2, 2u * w2_bytes);
+                for (int kb2 = 0; kb2 < p.q_kb; kb2++)
+                    tma_load_2d_cg2(w2 + (uint32_t)kb2 * w2_blk, &p.tmW2, bar_w2 & kPeerBitMask, kb2 * BK, (int)rank * (p.q_n / 2));
+            }
+            __syncwarp();
+        }
         if (patch) {
             // A-patch reuse: per (tile, 64-channel block) ONE patch of 130 + 2*Wp rows (this CTA's 128 output rows shifted by
             // -(Wp+1) .. +(Wp+1)) feeds all nine taps through row-shifted UMMA descriptors; only the weights ride the ring: the A
@@ -238,6 +257,27 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
     } else if (warp == 1) {
         if (rank == 0) {                                     // all 32 lanes run the loop; the MMAs / commits are elect-predicated
             uint32_t ti = 0, ms = 0, mph = 0, mps = 0, mpph = 0;
+            // chain fusion: the second MMA (A2 x W2 -> the TMEM stage the epilogue has just drained) of the PREVIOUS tile is issued
+            // from inside this tile's K loop as soon as the epilogue warps of both CTAs have written A2 (non-blocking test per stage),
+            // at the latest at the end of the K loop: the tensor pipe never waits for the epilogue, and the stage is handed back
+            // (second epilogue) before the tile after this one needs it.
+            bool pend = false, w2_ready = false;
+            uint32_t pend_as = 0, q_ph = 0;
+            const uint32_t IDESC2 = make_idesc(256, p.q_on ? p.q_n : BN);
+            auto issue_m2 = [&]() {
+                if (!w2_ready) { mbar_wait(bar_w2, 0u); w2_ready = true; }
+                tc_fence_after();
+                const uint32_t tacc2 = tmem_base + pend_as * (uint32_t)BN;
+                for (int kb2 = 0; kb2 < p.q_kb; kb2++) {
+                    const uint64_t da = make_smem_desc<SWZ>(a2 + (uint32_t)kb2 * 16384u);
+                    const uint64_t db = make_smem_desc<SWZ>(w2 + (uint32_t)kb2 * w2_blk);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                        umma_f16_cg2_elect(tacc2, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), IDESC2, (kb2 | k) ? 1u : 0u);
+                }
+                umma_commit_cg2_elect(bar_t2full);
+                pend = false; q_ph ^= 1u;
+            };
             for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters, ti++) {
                 const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
                 mbar_wait(bar_tempty + 8u * as, aph ^ 1u);                           // both CTAs' epilogues have drained this stage
@@ -254,6 +294,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                         for (int tap = 0; tap < 9; tap++) {
                             const uint32_t s = ms, ph = mph;
                             if (++ms == (uint32_t)S) { ms = 0; mph ^= 1u; }
+                            if (pend && mbar_test(bar_a2full, q_ph)) issue_m2();
                             mbar_wait(bar_full + 8u * s, ph);
                             tc_fence_after();
                             // patch row 0 is output row m0 shifted by -(Wp+1): tap (kh, kw) starts at row kh*Wp + kw
@@ -271,6 +312,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                 for (int kb0 = 0; kb0 < p.num_kb; kb0 += G) {
                     const uint32_t s = ms, ph = mph;
                     if (++ms == (uint32_t)S) { ms = 0; mph ^= 1u; }
+                    if (pend && mbar_test(bar_a2full, q_ph)) issue_m2();
                     mbar_wait(bar_full + 8u * s, ph);
                     tc_fence_after();
                     const int gcount = p.num_kb - kb0 < G ? p.num_kb - kb0 : G;
@@ -285,7 +327,10 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                     umma_commit_cg2_elect(bar_empty + 8u * s);
                 }
                 umma_commit_cg2_elect(bar_tfull + 8u * as);
+                if (pend) { mbar_wait(bar_a2full, q_ph); issue_m2(); }      // the previous tile's second MMA goes out before anything waits on its stage
+                if (p.q_on) { pend = true; pend_as = as; }
             }
+            if (pend) { mbar_wait(bar_a2full, q_ph); issue_m2(); }
         }
     } else {
         const int q = warp & 3;
@@ -300,12 +345,20 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
         const uint32_t my_slabs = slabs + (uint32_t)(warp - 2) * 2u * slab_bytes;
         if (p.epi && has_res && cluster_id < p.num_tiles)
             res_prefetch(p, my_slabs, tile_m0(cluster_id) + q * 32, tile_n0(cluster_id) + 32 * set, lane, gw64);
+        const bool chain = p.q_on != 0;
         for (int ct = cluster_id; ct < p.num_tiles; ct += nclusters, ti++) {
             const long long m0 = tile_m0(ct);
             const int n0 = tile_n0(ct);
             const uint32_t as = ti & 1u, aph = (ti >> 1) & 1u;
             const long long pr = m0 + r;
             bool valid = pr < p.M_total;
+            if (chain && has_res && ti > 0) {
+                // chain fusion: the second epilogue uses the slabs after the last group of a tile, so the skip tile of the next
+                // tile's first group cannot be prefetched across the tile boundary; it is requested here, before the wait on the MMAs
+                if (lane == 0) bulk_wait_read<0>();
+                __syncwarp();
+                res_prefetch(p, my_slabs + (sit & 1u) * slab_bytes, m0 + q * 32, n0 + 32 * set, lane, gw64);
+            }
             long long drow = 0;
             if (p.mode == 2) {
                 int bimg, boh0, bow0;
@@ -352,12 +405,24 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                 const uint32_t slab = my_slabs + (sit & 1u) * slab_bytes;
                 if (has_res && h == 0) { cp_async_wait_all(); __syncwarp(); }
                 epi_group(p, v, sbias + n0 + 32 * k, slab, lane, h, valid, has_res, gw64);
+                if (chain) {
+                    // the fp16 result chunk just written to the slab is also the second MMA's A operand: rows = this CTA's 128
+                    // pixels, 64-channel K blocks in the SWIZZLE_128B K-major layout
+                    const int c2 = n0 + 32 * k - p.q_col0;
+                    if (c2 >= 0 && c2 < 64 * p.q_kb) {
+                        const uint32_t blk = a2 + (uint32_t)(c2 >> 6) * 16384u + (uint32_t)r * 128u;
+                        const int ch0 = (c2 & 63) >> 3;
+#pragma unroll
+                        for (int j = 0; j < 4; j++)
+                            sts128(blk + (uint32_t)(((ch0 + j) ^ (r & 7)) << 4), lds128(slab_chunk_addr(slab, lane, 4 * h + j, gw64)));
+                    }
+                }
                 if (!last) return;
                 if (lane == 0) bulk_wait_read<0>();
                 __syncwarp();
                 if (has_res) {
                     int nk = gw64 ? k + 1 : k + NSETS, nct = ct;
-                    if (nk >= NCH || n0 + 32 * nk >= p.cout_store) { nk = set; nct = ct + nclusters; }
+                    if (nk >= NCH || n0 + 32 * nk >= p.cout_store) { nk = set; nct = chain ? p.num_tiles : ct + nclusters; }
                     if (nct < p.num_tiles)
                         res_prefetch(p, my_slabs + ((sit + 1u) & 1u) * slab_bytes, tile_m0(nct) + q * 32, tile_n0(nct) + 32 * nk, lane, gw64);
                 }
@@ -371,7 +436,8 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                 }
                 sit++;
             };
-            auto release_acc = [&]() { tc_fence_before(); if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * as); };
+            auto release_now = [&]() { tc_fence_before(); if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * as); };
+            auto release_acc = [&]() { if (!chain) release_now(); };      // chain fusion: the stage is handed back after the second epilogue
             if constexpr (NEPI == 8) {
 #pragma unroll 1
                 for (int k = set; k < NCH; k += NSETS) {
@@ -397,6 +463,39 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
                         __syncwarp();
                     }
                 }
+            }
+            if (chain) {
+                // A2 complete for this warp's groups: visible to the tensor core, then tell the leader's MMA warp
+                fence_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_leader(bar_a2full);
+                // ---- second epilogue: Q = 1x1 conv on the tile, accumulated into the same TMEM stage
+                mbar_wait(bar_t2full, ti & 1u);
+                tc_fence_after();
+                const int nch2 = p.q_n / 32;
+#pragma unroll 1
+                for (int k2 = set; k2 < nch2; k2 += NSETS) {
+                    tmem_ld32_issue(tacc + (uint32_t)(32 * k2), va);
+                    tmem_ld_wait(va);
+                    if (k2 + NSETS >= nch2) release_now();
+                    if (32 * k2 < p.q_cout_store) {
+                        const int h = gw64 ? (k2 & 1) : 0;
+                        const bool last = !gw64 || h == 1 || 32 * (k2 + 1) >= p.q_cout_store;
+                        const uint32_t slab = my_slabs + (sit & 1u) * slab_bytes;
+                        epi_group(p, va, sbias2 + 32 * k2, slab, lane, h, valid, false, gw64, p.q_act);
+                        if (last) {
+                            if (lane == 0) bulk_wait_read<0>();                      // as do_group: the other slab's store has drained
+                            __syncwarp();
+                            fence_async_smem();
+                            __syncwarp();
+                            if (lane == 0) { tma_store_2d(&p.tmOutQ, slab, 32 * (k2 - h), (int)(m0 + q * 32)); bulk_commit(); }
+                            sit++;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (set >= nch2) release_now();               // a warp set without a group of Q still owes its arrival
             }
         }
         if (p.epi && lane == 0) bulk_wait_all();
@@ -465,7 +564,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     const int ntaps = d.pairx ? 6 : d.k * d.k;
     if (d.raw_in || cin % 64 != 0 || d.split || d.out_f32 || d.upsample) return 0;
     const bool box = d.stride == 2;
-    if (d.out2 && box) return 0;
+    if ((d.out2 || d.q_on) && box) return 0;
     if (box ? (d.k != 3 || nepi != 4 || gw != 32) : (d.stride != 1)) return 0;
     if (d.cout_pad % bn || (nepi != 4 && nepi != 8)) return 0;
     if (!box && (d.cout % gw != 0 || (gw != 32 && (gw != 64 || nepi != 4)))) return 0;
@@ -542,7 +641,25 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     p.group = group;
     const size_t epi_bytes = box ? 0 : epi_slab_bytes(nepi, gw);
     size_t stage_bytes = ((size_t)128 * 64 * 2 + (size_t)(bn / 2) * 64 * 2) * group;
-    const size_t fixed = 1024 + epi_bytes + 16 * 8 + 192 + 4 * (size_t)d.cout_pad;
+    size_t chain_bytes = 0;
+    if (d.q_on) {
+        // chain fusion: one N tile must hold every channel Q reads; Q's N fits the accumulator stage; whole slab groups
+        if (d.cout_pad != bn || d.q_cin % 64 != 0 || d.q_col0 % 64 != 0 || d.q_col0 + d.q_cin > d.cout || d.q_cout_pad > bn ||
+            d.q_cout_pad % 32 != 0 || d.q_cout % gw != 0) return 0;
+        p.q_on = 1; p.q_kb = d.q_cin / 64; p.q_n = d.q_cout_pad; p.q_col0 = d.q_col0; p.q_cout_store = d.q_cout; p.q_act = d.q_act;
+        p.q_bias = d.q_bias;
+        cuuint64_t wdims[2] = {(cuuint64_t)d.q_cin, (cuuint64_t)d.q_cout_pad};
+        cuuint64_t wstr[1] = {(cuuint64_t)d.q_cin * 2};
+        cuuint32_t wbox[2] = {64, (cuuint32_t)(d.q_cout_pad / 2)};
+        if (!encode_map(&p.tmW2, const_cast<__half*>(d.q_w16), 2, wdims, wstr, wbox, 128, err)) return -1;
+        cuuint64_t qdims[2] = {(cuuint64_t)d.q_cout, (cuuint64_t)p.rows_alloc};
+        cuuint64_t qstr[1] = {(cuuint64_t)d.q_out_ld * 2};
+        cuuint32_t qbox[2] = {(cuuint32_t)gw, 32};
+        char* q_base = reinterpret_cast<char*>(d.q_out) + (size_t)d.q_out_choff * 2;
+        if (!encode_map(&p.tmOutQ, q_base, 2, qdims, qstr, qbox, gw * 2, err)) return -1;
+        chain_bytes = (size_t)p.q_kb * 16384 + (((size_t)p.q_kb * (size_t)(p.q_n / 2) * 128 + 1023) / 1024) * 1024;
+    }
+    const size_t fixed = 1024 + chain_bytes + epi_bytes + 16 * 8 + 224 + 4 * (size_t)d.cout_pad + 4 * (size_t)p.q_n;
     const size_t budget = (size_t)smem_budget_kb * 1024;
     size_t patch_total = 0;
     int S;
@@ -570,7 +687,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     P.stages = S; p.stages = S;
     p.n_tiles = d.cout_pad / bn;
     p.bias_n = d.cout_pad;
-    P.smem = 1024 + patch_total + S * stage_bytes + epi_bytes + 16 * S + 192 + 4 * (size_t)p.bias_n;
+    P.smem = 1024 + patch_total + S * stage_bytes + chain_bytes + epi_bytes + 16 * S + 224 + 4 * (size_t)p.bias_n + 4 * (size_t)p.q_n;
     if (P.smem > 225 * 1024) return 0;
     *pl = P;
     return P.kind;

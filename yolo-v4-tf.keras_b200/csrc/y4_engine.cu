@@ -71,6 +71,7 @@ struct ConvOp {
     float* d_wscale = nullptr;  // split precision: 1/s per cout (exact)
     __half* d_w16k32 = nullptr; // conv 0 only: [32][32], K zero-padded 27 -> 32 (conv0_tc.cuh)
     __half* d_w16_pair = nullptr; // 3x3 stride-2 conv with cin = 32 (conv 1): [cout_pad][6*64] for the pixel-pair view (TcConvDesc::pairx)
+    int chain = -1;                   // >= 0: the 1x1 conv with this index runs inside this conv's kernel, on the output tile (chain fusion)
     int fused_a = -1, fused_b = -1;   // >= 0: this entry is the sibling fusion of convs a and b (same input, one GEMM, cout = 2C):
     View out2;                        // columns [0, C) -> out (= a's destination), [C, 2C) -> out2 (= b's); appended after the 110 real convs
     int kind = 0;              // 0 simt, 1 tc flat, 2 tc box
@@ -773,6 +774,34 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
                 }
             }
         }
+        // Chain fusion (CTA-pair kernel, conv_tc2.cuh): a 1x1 conv whose input is exactly the tensor the previous launch produces
+        // (residual_block's first conv on the block input r_k, custom_layers.py:38-39; the first residual after csp_block's main
+        // 1x1) runs on the output tile while it is in shared memory: one launch, one read of r_k less.  Correct (bit-identical,
+        // tests/test_gpu_determinism.py) but NOT faster on B200: the fused kernel costs what the two launches cost (3x3 128->128 at 76^2:
+        // 0.109 ms vs 0.068 + 0.032) or more (1x1 producers: 0.63 vs 0.44 ms), because it removes HBM traffic while both epilogues (the
+        // actual bottleneck of the 1x1 layers) still run, now serialised on one tile's TMEM stage.  Opt-in: Y4_CHAIN=1.
+        if (!split && getenv("Y4_CHAIN") && getenv("Y4_CHAIN")[0] == '1') {
+            for (size_t k = 0; k + 1 < e->steps.size(); k++) {
+                if (e->steps[k].type != 0 || e->steps[k + 1].type != 0) continue;
+                const int pi = e->steps[k].conv, qi = e->steps[k + 1].conv;
+                ConvOp& P = e->convs[pi];
+                const ConvOp& Q = e->convs[qi];
+                if (P.kind != 1 || P.stride != 1 || P.out_f32 || P.upsample || P.chain >= 0) continue;
+                if (Q.k != 1 || Q.stride != 1 || Q.has_res || Q.upsample || Q.out_f32 || Q.fused_a >= 0 || Q.kind != 1) continue;
+                const View& src = P.fused_a >= 0 ? P.out2 : P.out;
+                if (Q.in.buf != src.buf || Q.in.choff != src.choff || Q.in.C != src.C) continue;
+                TcConvDesc d = P.desc;
+                const Buf& qb = e->bufs[Q.out.buf];
+                d.q_on = 1; d.q_w16 = Q.d_w16; d.q_bias = Q.d_bias; d.q_cin = Q.cin; d.q_cout = Q.cout; d.q_cout_pad = Q.cout_pad;
+                d.q_act = Q.act; d.q_col0 = P.fused_a >= 0 ? P.cout / 2 : 0;
+                d.q_out = qb.ptr; d.q_out_ld = qb.C; d.q_out_choff = Q.out.choff;
+                TcConvPlan pl;
+                std::string cerr2;
+                if (tc_plan2(d, &pl, &cerr2, P.cout_pad, 224, 2, 8, 32, 0) != 1) continue;
+                P.desc = d; P.tc = pl; P.chain = qi;
+                e->steps.erase(e->steps.begin() + k + 1);
+            }
+        }
         // Plan-time autotune, IN CONTEXT: every candidate configuration is planned for all layers it applies to, the whole
         // forward runs with per-layer CUDA events, and each layer keeps the plan that was fastest where it actually sits
         // (inputs in L2 or not, neighbours' tails) -- timing a layer alone on a hot L2 picked plans that lose in the pipeline.
@@ -1312,6 +1341,11 @@ int y4_describe_step(const y4_engine* e, int32_t step, y4_layer_info* info) {
         if (rc) return rc;
         const ConvOp& c = e->convs[st.conv];
         if (c.fused_a >= 0) info->flops = 2ll * c.N_OH * c.N_OH * c.cout * c.K;
+        if (c.chain >= 0) {
+            const ConvOp& q = e->convs[c.chain];
+            info->flops += 2ll * q.N_OH * q.N_OH * q.cout * q.K;
+            snprintf(info->out_name, sizeof(info->out_name), "%s>%s", c.out_name.c_str(), q.out_name.c_str());
+        }
         return Y4_OK;
     }
     memset(info, 0, sizeof(*info));
