@@ -569,10 +569,10 @@ __device__ __forceinline__ void epi_group(const TcParams& p, const uint32_t (&v)
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// LEAN (NEPI = 4, BN = 64): the single-buffer epilogue loop compiled for FOUR 192-thread CTAs per SM (<= 85 registers):
-// as many epilogue warps per SM as two 8-warp CTAs, but four independent tile pipelines.
+// LEAN (NEPI = 4, BN = 64): the single-buffer epilogue loop compiled for THREE 192-thread CTAs per SM (<= 113 registers):
+// more epilogue warps per SM than two 8-warp CTAs, and three independent tile pipelines.
 template <int BN, int BK, bool SPLIT, int NEPI, bool LEAN = false>
-__global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 4 : 2)) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 3 : 2)) conv_tc_kernel(const __grid_constant__ TcParams p) {
     static_assert(NEPI == 4 || NEPI == 8, "4 or 8 epilogue warps");
     static_assert(!SPLIT || BN / (NEPI / 4) <= 64, "split precision: each epilogue warp sums at most 64 accumulator columns in registers");
     static_assert(!LEAN || (NEPI == 4 && !SPLIT && BN == 64), "lean 4-CTA/SM variant: 64-wide tiles, slab epilogue only");
@@ -1368,7 +1368,8 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     int cps = (int)((227 * 1024) / (P.smem + 1024));            // +1 KB: per-CTA reserved shared memory
     const int tmem_cols = 2 * bn;
     if (cps > 512 / tmem_cols) cps = 512 / tmem_cols;            // two accumulator stages per CTA must all fit in TMEM
-    if (cps > (lean ? 4 : 2)) cps = lean ? 4 : 2;                // register file: 168 regs x 192 threads (85 for the lean variant)
+    if (cps > (lean ? 3 : 2)) cps = lean ? 3 : 2;                // register file: 168 regs x 192 threads (113 for the lean variant: shared memory
+                                                                 // never let a fourth CTA in, and 80 registers starved the epilogue of ILP -- stall 'wait' 35 %)
     if (cps < 1) cps = 1;
     if (d.split) cps = 1;                                       // split kernels use > 170 registers/thread
     P.ctas_per_sm = cps;
