@@ -364,7 +364,7 @@ def main():
     dn_bytes = B * (eng.num_boxes * (5 + eng.num_classes) * 4 + eng.max_boxes * 24 + 4)
     decode_nms = {'bound': 'hbm', 'us_per_img': 1e3 * dn_ms / B, 'ms_per_batch': dn_ms, 'algorithmic_bytes_per_batch': dn_bytes,
                   'achieved': dn_bytes / dn_ms / 1e6, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': dn_bytes / dn_ms / 1e6 / pk['hbm_gbs'],
-                  'kernels': 'decode_filter + nms_bucket + nms_class + nms_overflow + nms_merge (graph replay, CUDA events)'}
+                  'kernels': 'decode_filter + nms_image + nms_overflow + nms_merge (graph replay, CUDA events)'}
 
     # ---- e2e through the C-ABI with host buffers --------------------------------------------------
     imgs = binding.pinned_array((B, S, S, 3))

@@ -65,7 +65,7 @@ line = {'workload': f'configs[3]: decode+NMS isolation, {size}x{size} heads, bat
         'cpu_us_per_img': 1e6 * cpu_s / n_ref, 'cpu_nms_only_us_per_img': 1e6 * cpu_nms_s / n_ref,
         'cpu_what': 'numpy decode + C/OpenMP restatement of combined_non_max_suppression (oracle/nms_ref.c), all host cores, whole batch',
         'cpu_python_oracle_us_per_img': 1e6 * py_s / 2, 'cpu_cores': len(os.sched_getaffinity(0)), 'images_compared': n_ref,
-        'indices_classes_valid_bit_exact': bool(exact), 'max_abs_diff_boxes_scores': coord, 'launches_per_batch': 5}
+        'indices_classes_valid_bit_exact': bool(exact), 'max_abs_diff_boxes_scores': coord, 'launches_per_batch': 4}
 print(json.dumps(line))
 os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
 with open(os.path.join(ROOT, 'gpurun_out', 'decode_nms.json'), 'w') as f:

@@ -47,6 +47,9 @@ struct TcConvDesc {
     // memory: Q's input = this conv's output columns [q_col0, q_col0 + q_cin)
     int q_on; const __half* q_w16; const float* q_bias; int q_cin, q_cout, q_cout_pad, q_act, q_col0;
     void* q_out; int q_out_ld, q_out_choff;
+    // head convs (fp32 out): the objectness logits (channel obj_c0 + a * obj_stride, a = 0..2) are ALSO written to a compact
+    // planar array [3][rows] so that the decode kernel's first pass reads them coalesced instead of one 32 B sector per box
+    float* obj_out; int obj_c0, obj_stride; long long obj_rows;
     // pixel-pair view for a 3x3 stride-2 conv with cin = 32 (conv 1): two neighbouring pixels = 64 contiguous channels, so the taps
     // (kh, kw=0|1) are ONE 128 B-row box and (kh, kw=2|zero) another: 6 taps of 64 instead of 9 of 32 (w16_pair: [cout_pad][6*64])
     int pairx; const __half* w16_pair;
@@ -100,6 +103,7 @@ struct TcParams {
     int OH, OW, TH, TW, tiles_w, tiles_per_img;
     int pairx;                   // box mode over the pixel-pair view: tap t = (kh, j): plane (kh & 1, 0), x offset j, y offset kh >> 1
     long long* dbg;              // optional per-CTA phase timestamps (y4_debug_trace_conv); nullptr in production
+    float* obj_out; int obj_c0, obj_stride; long long obj_rows;   // head convs: compact copy of the objectness logits (TcConvDesc)
 };
 
 struct TcConvPlan {
@@ -421,6 +425,20 @@ __device__ __forceinline__ void add_half32(const uint4 (&r)[4], float (&f)[32]) 
     }
 }
 
+// head convs: copy the objectness logits among columns [col0, col0 + 32) of pixel row `grow` to the compact planar array
+__device__ __forceinline__ void obj_side_write(const TcParams& p, const float (&f)[32], int col0, long long grow) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const int c = p.obj_c0 + a * p.obj_stride - col0;
+        if (c >= 0 && c < 32) {                             // warp-uniform
+            float v = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j++) v = (j == c) ? f[j] : v;
+            p.obj_out[a * p.obj_rows + grow] = v;
+        }
+    }
+}
+
 // One 32-column chunk of the epilogue for one accumulator row: (*scale) + bias -> activation -> (+skip) -> store.
 // Split precision: the skip tile is hi + lo, and the result is stored as hi = fp16(x), lo = fp16(x - hi).
 template <bool SPLIT>
@@ -464,6 +482,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
         float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + drow * p.out_ld + p.out_choff + col0);
 #pragma unroll
         for (int j = 0; j < 8; j++) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        if (p.obj_out) obj_side_write(p, f, col0, drow);
         return;
     }
     float g[32];                                           // split: residual x - fp16(x), exactly representable difference
@@ -525,7 +544,7 @@ __device__ __forceinline__ void res_prefetch(const TcParams& p, uint32_t slab, l
 
 // 32 accumulator columns of this thread's row -> activation (-> + skip chunk from the slab) -> fp16 -> slab chunks 4h..4h+3
 __device__ __forceinline__ void epi_group(const TcParams& p, const uint32_t (&v)[32], const float* sb, uint32_t slab, int lane, int h,
-                                          bool interior, bool has_res, bool gw64, int act_sel = -1) {
+                                          bool interior, bool has_res, bool gw64, int act_sel = -1, int col0 = 0, long long grow = 0) {
     float f[32];
     const int act = act_sel < 0 ? p.act : act_sel;          // chain fusion: the second conv's activation
     if (act == 2) act32_fast<2>(v, sb, f);
@@ -538,6 +557,7 @@ __device__ __forceinline__ void epi_group(const TcParams& p, const uint32_t (&v)
             if (!interior) o = make_uint4(0u, 0u, 0u, 0u);
             sts128(slab_chunk_addr(slab, lane, j, true), o);
         }
+        if (p.obj_out && interior) obj_side_write(p, f, col0, grow);
         return;
     }
 #pragma unroll
@@ -983,7 +1003,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 3 : 2)) co
                     const bool last = !gw64 || h == 1 || tc.n0 + 32 * (k + 1) >= p.cout_store;
                     const uint32_t slab = my_slabs + (sit & 1u) * slab_bytes;
                     if (has_res && h == 0) { cp_async_wait_all(); __syncwarp(); }
-                    epi_group(p, v, sbias + tc.n0 + 32 * k, slab, lane, h, valid, has_res, gw64);
+                    epi_group(p, v, sbias + tc.n0 + 32 * k, slab, lane, h, valid, has_res, gw64, -1, tc.n0 + 32 * k, tc.m0 + r);
                     if (!last) return;
                     if (lane == 0) bulk_wait_read<0>();                      // the previous group's store has drained its slab
                     __syncwarp();
@@ -1220,6 +1240,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     }
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
     p.act = d.act; p.out_f32 = d.out_f32; p.upsample = d.upsample;
+    if (d.out_f32 && d.obj_out) { p.obj_out = d.obj_out; p.obj_c0 = d.obj_c0; p.obj_stride = d.obj_stride; p.obj_rows = d.obj_rows; }
     if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);
     if (getenv("Y4_DEBUG_NORES")) p.res = nullptr;                          // timing experiments only (wrong results)
     p.cout_store = d.out_f32 ? d.cout_pad : d.cout;

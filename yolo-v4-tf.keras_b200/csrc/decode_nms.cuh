@@ -29,6 +29,8 @@ struct DecodeParams {
     int batch;
     float img_size;
     float score_thr;
+    const float* obj[3];             // optional compact planar copy of the objectness logits, [3][obj_rows[s]] over the padded-flat
+    long long obj_rows[3];           // pixel rows (written by the head convs' epilogue): the first pass then reads coalesced
     unsigned long long* cand_keys;   // [batch][kCandCap]
     int* cand_count;                 // [batch]
     float4* boxes;                   // [batch][N] normalised x1,y1,x2,y2 (written only for boxes with a candidate)
@@ -61,68 +63,117 @@ __device__ __forceinline__ const float* box_logits(const DecodeParams& p, int im
     return cellp + a * p.C;
 }
 
-// One thread per box (cell, anchor): objectness test first (score = obj * cls <= obj since cls <= 1 and the product is
-// rounded to nearest, so a box whose objectness fails can produce no candidate).  The few boxes that pass are then expanded
-// by the whole warp, one after the other: lanes take the classes, candidates are appended with one atomic per ballot, and
-// the box is decoded once if any class passed.  (The earlier warp-per-cell version spent its time launching 240 k warps per
-// batch that exit after three loads.)
-__global__ void __launch_bounds__(256) decode_filter_kernel(DecodeParams p) {
-    const int lane = threadIdx.x & 31;
-    const long long gt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)p.batch * p.N;
-    int img = 0, n = 0, s = 0, a = 0, row = 0, col = 0;
-    const float* q = nullptr;
-    float obj = 0.f;
+// Two phases per CTA of 256 boxes of ONE image (grid.y = image):
+//  1. one thread per box tests objectness (score = obj * cls <= obj since cls <= 1 and the product is rounded to nearest, so a
+//     box whose objectness fails can produce no candidate); the logits come from the compact planar copy the head convs write
+//     (coalesced) when there is one.  The boxes that pass are compacted into a shared list.
+//  2. the CTA's eight warps share that list evenly: one warp per box reads the whole 5 + nc row with every load in flight at
+//     once (3 coalesced loads at 80 classes), lanes take the classes, lanes 0-3 decode the box.  Candidates are staged in shared
+//     memory and appended to the image's list with ONE global atomic per CTA (keys that do not fit the stage -- more than
+//     kStageKeys candidates among 256 boxes -- go out one by one).
+// 64-bit keys `class | ~score_bits | box`; the order inside the list is arbitrary (nms_image_kernel sorts).
+constexpr int kFilterThreads = 256;
+constexpr int kStageKeys = 1024;
+__global__ void __launch_bounds__(kFilterThreads) decode_filter_kernel(DecodeParams p) {
+    __shared__ unsigned long long s_keys[kStageKeys];
+    __shared__ int s_list[kFilterThreads];
+    __shared__ int s_npass, s_nkeys, s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int img = blockIdx.y;
+    const int n = blockIdx.x * kFilterThreads + tid;
+    if (tid == 0) { s_npass = 0; s_nkeys = 0; }
+    __syncthreads();
     bool pass = false;
-    if (gt < total) {
-        img = (int)(gt / p.N);
-        n = (int)(gt - (long long)img * p.N);
-        q = box_logits(p, img, n, s, a, row, col);
-        obj = sigmoid_rn(q[4]);
-        pass = obj > p.score_thr;
+    if (n < p.N) {
+        int s, a, row, col;
+        const float* q = box_logits(p, img, n, s, a, row, col);
+        const float lo = p.obj[s] ? p.obj[s][a * p.obj_rows[s] + ((long long)img * (p.g[s] + 2) + row + 1) * (p.g[s] + 2) + col + 1] : q[4];
+        pass = sigmoid_rn(lo) > p.score_thr;
     }
-    unsigned todo = __ballot_sync(0xffffffffu, pass);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const float* bq = reinterpret_cast<const float*>(__shfl_sync(0xffffffffu, (unsigned long long)q, src));
-        const float bobj = __shfl_sync(0xffffffffu, obj, src);
-        const int bimg = __shfl_sync(0xffffffffu, img, src), bn = __shfl_sync(0xffffffffu, n, src);
+    {
+        const unsigned m = __ballot_sync(0xffffffffu, pass);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&s_npass, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) s_list[base + __popc(m & lt)] = n;
+        }
+    }
+    __syncthreads();
+    const int npass = s_npass;
+    for (int it = warp; it < npass; it += kFilterThreads / 32) {
+        const int bn = s_list[it];
+        int s, a, row, col;
+        const float* q = box_logits(p, img, bn, s, a, row, col);
         bool any = false;
-        for (int f0 = 0; f0 < p.nc; f0 += 32) {
-            const int f = f0 + lane;
-            bool cand = false;
-            float score = 0.f;
-            if (f < p.nc) {
-                score = __fmul_rn(bobj, sigmoid_rn(bq[5 + f]));          // confidence * class_probabilities (custom_layers.py:282)
-                cand = score > p.score_thr;                               // strict >
+        float v0 = 0.f, bobj = 0.f;
+        for (int k0 = 0; k0 < p.C; k0 += 96) {
+            float v[3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) { const int idx = k0 + 32 * k + lane; v[k] = idx < p.C ? q[idx] : 0.f; }
+            if (k0 == 0) { v0 = v[0]; bobj = sigmoid_rn(__shfl_sync(0xffffffffu, v0, 4)); }
+            unsigned mk[3];
+            float sc[3];
+            int tot = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int f = k0 + 32 * k + lane - 5;
+                bool cand = false;
+                sc[k] = 0.f;
+                if (f >= 0 && f < p.nc) {
+                    sc[k] = __fmul_rn(bobj, sigmoid_rn(v[k]));                // confidence * class_probabilities (custom_layers.py:282)
+                    cand = sc[k] > p.score_thr;                               // strict >
+                }
+                mk[k] = __ballot_sync(0xffffffffu, cand);
+                tot += __popc(mk[k]);
             }
-            const unsigned mask = __ballot_sync(0xffffffffu, cand);
-            if (mask) {
+            if (tot) {
                 any = true;
                 int base = 0;
-                if (lane == 0) base = atomicAdd(&p.cand_count[bimg], __popc(mask));
+                if (lane == 0) base = atomicAdd(&s_nkeys, tot);
                 base = __shfl_sync(0xffffffffu, base, 0);
-                if (cand) {
-                    const int pos = base + __popc(mask & ((1u << lane) - 1u));
-                    if (pos < kCandCap) p.cand_keys[(long long)bimg * kCandCap + pos] = cand_key(f, score, bn);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if ((mk[k] >> lane) & 1u) {
+                        const int pos = base + __popc(mk[k] & lt);
+                        const unsigned long long key = cand_key(k0 + 32 * k + lane - 5, sc[k], bn);
+                        if (pos < kStageKeys) s_keys[pos] = key;
+                        else {                                                // stage full: straight to the image's list
+                            const int gpos = atomicAdd(&p.cand_count[img], 1);
+                            if (gpos < kCandCap) p.cand_keys[(long long)img * kCandCap + gpos] = key;
+                        }
+                    }
+                    base += __popc(mk[k]);
                 }
             }
         }
-        if (any && lane == src) {
-            const float sx = sigmoid_rn(q[0]), sy = sigmoid_rn(q[1]);
-            const float bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, p.xyscale[s]), p.xyoff[s]), (float)col), p.stride[s]);
-            const float by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, p.xyscale[s]), p.xyoff[s]), (float)row), p.stride[s]);
-            const float bw = __fmul_rn(expf(q[2]), p.anchors[(s * 3 + a) * 2 + 0]);
-            const float bh = __fmul_rn(expf(q[3]), p.anchors[(s * 3 + a) * 2 + 1]);
-            const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);   // box_wh / 2 (exact)
-            float4 b;
-            b.x = __fdiv_rn(__fsub_rn(bx, hw), p.img_size);                   // boxes / input_shape[0]  (custom_layers.py:284)
-            b.y = __fdiv_rn(__fsub_rn(by, hh), p.img_size);
-            b.z = __fdiv_rn(__fadd_rn(bx, hw), p.img_size);
-            b.w = __fdiv_rn(__fadd_rn(by, hh), p.img_size);
-            p.boxes[(long long)img * p.N + n] = b;
+        if (any) {                                                            // warp-uniform
+            const float t = lane < 2 ? sigmoid_rn(v0) : expf(v0);             // lanes 0..3 hold the x, y, w, h logits
+            const float sx = __shfl_sync(0xffffffffu, t, 0), sy = __shfl_sync(0xffffffffu, t, 1);
+            const float ew = __shfl_sync(0xffffffffu, t, 2), eh = __shfl_sync(0xffffffffu, t, 3);
+            if (lane == 0) {
+                const float bx = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, p.xyscale[s]), p.xyoff[s]), (float)col), p.stride[s]);
+                const float by = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, p.xyscale[s]), p.xyoff[s]), (float)row), p.stride[s]);
+                const float bw = __fmul_rn(ew, p.anchors[(s * 3 + a) * 2 + 0]);
+                const float bh = __fmul_rn(eh, p.anchors[(s * 3 + a) * 2 + 1]);
+                const float hw = __fmul_rn(bw, 0.5f), hh = __fmul_rn(bh, 0.5f);   // box_wh / 2 (exact)
+                float4 b;
+                b.x = __fdiv_rn(__fsub_rn(bx, hw), p.img_size);                   // boxes / input_shape[0]  (custom_layers.py:284)
+                b.y = __fdiv_rn(__fsub_rn(by, hh), p.img_size);
+                b.z = __fdiv_rn(__fadd_rn(bx, hw), p.img_size);
+                b.w = __fdiv_rn(__fadd_rn(by, hh), p.img_size);
+                p.boxes[(long long)img * p.N + bn] = b;
+            }
         }
+    }
+    __syncthreads();
+    const int nk = s_nkeys < kStageKeys ? s_nkeys : kStageKeys;
+    if (tid == 0 && nk > 0) s_base = atomicAdd(&p.cand_count[img], nk);
+    __syncthreads();
+    for (int i = tid; i < nk; i += kFilterThreads) {
+        const int pos = s_base + i;
+        if (pos < kCandCap) p.cand_keys[(long long)img * kCandCap + pos] = s_keys[i];
     }
 }
 
@@ -143,13 +194,11 @@ struct NmsParams {
     const int* cand_count;                 // [batch]
     const float4* boxes;                   // [batch][N]
     int N, nc, max_boxes;
+    int merge_batch;                       // images in this launch (nms_merge_kernel: several images per CTA)
     float iou_thr;
     // workspace
-    unsigned long long* bucket_keys;       // [batch][kCandCap]   grouped by class (order inside a class arbitrary)
-    unsigned long long* sorted_keys;       // [batch][kCandCap]   only used by class segments longer than kClassSmemKeys
-    int* seg_start;                        // [batch][257]        first bucket position of each class
     unsigned long long* win_keys;          // [batch][nc][max_boxes]  per-class NMS survivors as merge keys, score descending
-    int* nwin;                             // [batch][256]
+    int* nwin;                             // [batch][256]              (both only for images on the overflow path)
     float* out_boxes;      // [batch][max_boxes][4]
     float* out_scores;     // [batch][max_boxes]
     float* out_classes;    // [batch][max_boxes]
@@ -157,18 +206,19 @@ struct NmsParams {
     int* out_idx;          // [batch][max_boxes]
 };
 
-// combined_non_max_suppression as three small kernels whose parallelism is (image, class), not image:
-//   nms_bucket_kernel  one CTA per image: counting sort of the candidate keys by class (smem histogram + scatter)
-//   nms_class_kernel   one CTA per (image, class): rank sort of the segment (score desc, box asc; keys are unique),
-//                      then warp 0 runs TF's greedy scan (iou > thr strict, against already selected boxes)
-//                      (segments longer than kClassSmemKeys: greedy by repeated block-wide arg-max, no sort)
-//   nms_overflow_kernel one CTA per (image, class), only for images whose candidates did not fit kCandCap: the same greedy
-//                      selection by repeated arg-max straight from the head tensors -- exact for ANY number of candidates
-//   nms_merge_kernel   one CTA per image: k-way merge of the per-class survivor lists, first max_boxes, clipped to [0,1]
-constexpr int kBucketThreads = 1024;
-constexpr int kClassThreads = 128;
-constexpr int kClassSmemKeys = 1024;
-constexpr int kMergeThreads = 256;                            // >= num_classes (255 max): one thread per class list
+// combined_non_max_suppression:
+//   nms_image_kernel    ONE CTA per image does everything in shared memory for images whose candidates fit kCandCap (all of them
+//                       at the usual thresholds): bitonic sort of the keys (class asc, score desc, box asc) -> class segments ->
+//                       one warp per class runs TF's greedy scan (iou > thr strict, against already selected boxes) on boxes
+//                       held in shared memory -> survivors become merge keys in place -> second bitonic sort -> the first
+//                       max_boxes, clipped to [0,1].  (Round 2a ran this as bucket / class / merge kernels with (image, class)
+//                       CTAs: 5 dependent launches and three global round trips, ~100 us per batch of 32; this is ~15.)
+//   nms_overflow_kernel one CTA per (image, class), only for images whose candidates did not fit kCandCap: greedy selection by
+//                       repeated arg-max straight from the head tensors -- exact for ANY number of candidates
+//   nms_merge_kernel    one warp per overflow image: k-way merge of the per-class survivor lists, first max_boxes, clipped
+constexpr int kImgThreads = 1024;
+constexpr int kMergeThreads = 256;
+constexpr size_t kImgSmemBytes = (size_t)kCandCap * (8 + 16) + (kImgThreads / 32) * kMaxBoxesCap * sizeof(unsigned short);
 
 // block-wide minimum of a 64-bit key, result in every thread (T threads, all participate; contains two barriers)
 template <int T>
@@ -185,133 +235,140 @@ __device__ __forceinline__ unsigned long long block_min_u64(unsigned long long v
     return best;
 }
 
-__global__ void __launch_bounds__(kBucketThreads) nms_bucket_kernel(NmsParams p) {
-    __shared__ int hist[256], cursor[256];
-    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    int cnt = p.cand_count[img];
-    if (cnt > kCandCap) cnt = kCandCap;                     // this image is redone exactly by nms_overflow_kernel
-    if (tid < 256) hist[tid] = 0;
-    __syncthreads();
-    constexpr int PER = kCandCap / kBucketThreads;
-    unsigned long long k[PER];
-#pragma unroll
-    for (int r = 0; r < PER; r++) {
-        const int i = tid + r * kBucketThreads;
-        if (i < cnt) { k[r] = p.cand_keys[(long long)img * kCandCap + i]; atomicAdd(&hist[(int)(k[r] >> 56)], 1); }
-    }
-    __syncthreads();
-    if (tid < 32) {                                        // exclusive scan of the 256 bins, 8 per lane
-        int v[8], s = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { v[j] = hist[lane * 8 + j]; s += v[j]; }
-        int incl = s;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += t; }
-        int run = incl - s;
-#pragma unroll
-        for (int j = 0; j < 8; j++) { cursor[lane * 8 + j] = run; p.seg_start[img * 257 + lane * 8 + j] = run; run += v[j]; }
-        if (lane == 31) p.seg_start[img * 257 + 256] = run;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int r = 0; r < PER; r++) {
-        const int i = tid + r * kBucketThreads;
-        if (i < cnt) p.bucket_keys[(long long)img * kCandCap + atomicAdd(&cursor[(int)(k[r] >> 56)], 1)] = k[r];
+// Ascending bitonic sort of s[0..n) in shared memory, n a power of two >= 32, called by all T threads.  Exchange distances of 32
+// and more go through shared memory (one barrier each); the distances below 32 of a merge step stay inside a warp and run on
+// shuffles (one barrier per step): 15 + 10 barriers instead of 55 at n = 1024.
+template <int T>
+__device__ __forceinline__ void bitonic_sort_smem(unsigned long long* s, int n) {
+    const int tid = threadIdx.x;
+    for (int k = 2; k <= n; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= 32; j >>= 1) {
+            for (int t = tid; t < (n >> 1); t += T) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));      // zero bit inserted at log2(j)
+                const int l = i | j;
+                const unsigned long long a = s[i], b = s[l];
+                if ((a > b) == ((i & k) == 0)) { s[i] = b; s[l] = a; }
+            }
+            __syncthreads();
+        }
+        for (int i = tid; i < n; i += T) {                                // whole warps: n and T are multiples of 32
+            unsigned long long v = s[i];
+            const bool asc = (i & k) == 0;
+            for (int jj = j; jj > 0; jj >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, jj);
+                const bool keep_min = ((i & jj) == 0) == asc;
+                v = keep_min ? (o < v ? o : v) : (o > v ? o : v);
+            }
+            s[i] = v;
+        }
+        __syncthreads();
     }
 }
 
-__global__ void __launch_bounds__(kClassThreads) nms_class_kernel(NmsParams p) {
-    __shared__ unsigned long long sin[kClassSmemKeys], ssorted[kClassSmemKeys];
-    __shared__ float4 selbox[kMaxBoxesCap];
-    const int img = blockIdx.x / p.nc, c = blockIdx.x - img * p.nc;
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (p.cand_count[img] > kCandCap) return;              // truncated candidate list: nms_overflow_kernel owns this image
-    const int lo = p.seg_start[img * 257 + c], L = p.seg_start[img * 257 + c + 1] - lo;
-    if (L == 0) { if (tid == 0) p.nwin[img * 256 + c] = 0; return; }
-    const unsigned long long* in = p.bucket_keys + (long long)img * kCandCap + lo;
-    unsigned long long* sorted = p.sorted_keys + (long long)img * kCandCap + lo;
-    if (L > kClassSmemKeys) {
-        // long segment (up to kCandCap keys of one class): sorting it would cost O(L^2) (rank sort) for at most max_boxes picks;
-        // greedy selection by arg-max rounds instead: round r suppresses against the box picked in round r-1 and finds the
-        // best remaining key, <= max_boxes passes over the segment, alive bits in shared memory
-        __shared__ unsigned dead[kCandCap / 32];
-        const int words = (L + 31) >> 5;
-        for (int w = tid; w < words; w += kClassThreads) dead[w] = (w * 32 + 32 <= L) ? 0u : ~((1u << (L - w * 32)) - 1u);
-        __syncthreads();
-        const float4* bx = p.boxes + (long long)img * p.N;
-        unsigned long long* wk = p.win_keys + ((long long)img * p.nc + c) * p.max_boxes;
-        float4 sel = make_float4(0.f, 0.f, 0.f, 0.f);
-        int ns = 0;
-        while (ns < p.max_boxes) {
-            unsigned long long mine = ~0ull;
-            int mypos = 0;
-            for (int w = tid; w < words; w += kClassThreads) {
-                unsigned m = ~dead[w], kill = 0u;
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    const unsigned long long k = in[w * 32 + b];
-                    if (ns > 0 && iou_tf(bx[(int)(k & 0xFFFFFFull)], sel) > p.iou_thr) { kill |= 1u << b; continue; }   // strict >
-                    if (k < mine) { mine = k; mypos = w * 32 + b; }
-                }
-                dead[w] |= kill;
-            }
-            const unsigned long long best = block_min_u64<kClassThreads>(mine);
-            if (best == ~0ull) break;
-            const int box = (int)(best & 0xFFFFFFull);
-            if (mine == best) {                             // keys are unique: exactly one owner, and it owns that word of dead[]
-                wk[ns] = merge_key(c, __uint_as_float(~(unsigned)((best >> 24) & 0xFFFFFFFFull)), box);
-                dead[mypos >> 5] |= 1u << (mypos & 31);
-            }
-            sel = bx[box];
-            ns++;
-            __syncthreads();
-        }
-        if (tid == 0) p.nwin[img * 256 + c] = ns;
-        return;
-    }
-    if (L <= kClassSmemKeys) {
-        for (int i = tid; i < L; i += kClassThreads) sin[i] = in[i];
-        __syncthreads();
-        in = sin; sorted = ssorted;
-    }
-    for (int i = tid; i < L; i += kClassThreads) {        // keys are unique (box index): rank = number of smaller keys
-        const unsigned long long k = in[i];
-        int r = 0;
-        for (int j = 0; j < L; j++) r += in[j] < k;
-        sorted[r] = k;
+__global__ void __launch_bounds__(kImgThreads, 1) nms_image_kernel(NmsParams p) {
+    extern __shared__ __align__(16) unsigned char nms_smem[];
+    unsigned long long* skey = reinterpret_cast<unsigned long long*>(nms_smem);                 // [n_pad] sort keys, later merge keys
+    float4* sbox = reinterpret_cast<float4*>(nms_smem + (size_t)kCandCap * 8);                  // [cnt] boxes in sorted order
+    unsigned short* selpos_all = reinterpret_cast<unsigned short*>(nms_smem + (size_t)kCandCap * 24);
+    __shared__ int seg_lo[256], seg_hi[256];
+    __shared__ int next_class;
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cnt = p.cand_count[img];
+    if (cnt > kCandCap) return;                            // nms_overflow_kernel + nms_merge_kernel own this image
+    int n_pad = 32;
+    while (n_pad < cnt) n_pad <<= 1;
+    for (int i = tid; i < n_pad; i += kImgThreads) skey[i] = i < cnt ? p.cand_keys[(long long)img * kCandCap + i] : ~0ull;
+    if (tid < 256) { seg_lo[tid] = 0; seg_hi[tid] = 0; }
+    if (tid == 0) next_class = 0;
+    __syncthreads();
+    bitonic_sort_smem<kImgThreads>(skey, n_pad);
+    for (int i = tid; i < cnt; i += kImgThreads) {
+        const unsigned long long k = skey[i];
+        const int c = (int)(k >> 56);
+        sbox[i] = p.boxes[(long long)img * p.N + (int)(k & 0xFFFFFFull)];
+        if (i == 0 || (int)(skey[i - 1] >> 56) != c) seg_lo[c] = i;
+        if (i == cnt - 1 || (int)(skey[i + 1] >> 56) != c) seg_hi[c] = i + 1;
     }
     __syncthreads();
-    if (tid >= 32) return;
-
-    const float4* boxes = p.boxes + (long long)img * p.N;
-    unsigned long long* win = p.win_keys + ((long long)img * p.nc + c) * p.max_boxes;
-    int nsel = 0;
-    for (int base = 0; base < L && nsel < p.max_boxes; base += 32) {
-        const int mine = base + lane;
-        unsigned long long mykey = 0ull;
-        float4 mybx = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (mine < L) { mykey = sorted[mine]; mybx = boxes[(int)(mykey & 0xFFFFFFull)]; }
-        const int cnt32 = L - base < 32 ? L - base : 32;
-        for (int j = 0; j < cnt32 && nsel < p.max_boxes; j++) {
-            float4 b;
-            b.x = __shfl_sync(0xffffffffu, mybx.x, j); b.y = __shfl_sync(0xffffffffu, mybx.y, j);
-            b.z = __shfl_sync(0xffffffffu, mybx.z, j); b.w = __shfl_sync(0xffffffffu, mybx.w, j);
-            const unsigned long long key = __shfl_sync(0xffffffffu, mykey, j);
-            bool sup = false;
-            for (int t = lane; t < nsel; t += 32) sup |= iou_tf(b, selbox[t]) > p.iou_thr;   // strict >
-            if (!__any_sync(0xffffffffu, sup)) {
-                if (lane == 0) {
-                    selbox[nsel] = b;
-                    const float score = __uint_as_float(~(unsigned)((key >> 24) & 0xFFFFFFFFull));
-                    win[nsel] = merge_key(c, score, (int)(key & 0xFFFFFFull));
+    unsigned short* selpos = selpos_all + warp * kMaxBoxesCap;
+    while (true) {                                          // one warp per class, classes handed out dynamically
+        int c = 0;
+        if (lane == 0) c = atomicAdd(&next_class, 1);
+        c = __shfl_sync(0xffffffffu, c, 0);
+        if (c >= p.nc) break;
+        const int lo = seg_lo[c], L = seg_hi[c] - lo;
+        if (L == 0) continue;
+        int nsel = 0, base = 0;
+        if (L <= 32) {                                      // the usual case: the selected boxes are a lane mask, no shared list
+            const float4 mb = lane < L ? sbox[lo + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+            unsigned selmask = 0u;
+            for (int j = 0; j < L && nsel < p.max_boxes; j++) {
+                float4 b;
+                b.x = __shfl_sync(0xffffffffu, mb.x, j); b.y = __shfl_sync(0xffffffffu, mb.y, j);
+                b.z = __shfl_sync(0xffffffffu, mb.z, j); b.w = __shfl_sync(0xffffffffu, mb.w, j);
+                const bool sup = ((selmask >> lane) & 1u) && iou_tf(b, mb) > p.iou_thr;      // strict >
+                if (!__any_sync(0xffffffffu, sup)) { selmask |= 1u << j; nsel++; }
+            }
+            if (lane < L) {
+                const unsigned long long k = skey[lo + lane];
+                skey[lo + lane] = ((selmask >> lane) & 1u)
+                    ? merge_key(c, __uint_as_float(~(unsigned)((k >> 24) & 0xFFFFFFFFull)), (int)(k & 0xFFFFFFull)) : ~0ull;
+            }
+            continue;
+        }
+        for (; base < L && nsel < p.max_boxes; base += 32) {
+            const int mine = base + lane;
+            const float4 mb = mine < L ? sbox[lo + mine] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int cnt32 = L - base < 32 ? L - base : 32;
+            unsigned keep = 0u;
+            for (int j = 0; j < cnt32 && nsel < p.max_boxes; j++) {
+                float4 b;
+                b.x = __shfl_sync(0xffffffffu, mb.x, j); b.y = __shfl_sync(0xffffffffu, mb.y, j);
+                b.z = __shfl_sync(0xffffffffu, mb.z, j); b.w = __shfl_sync(0xffffffffu, mb.w, j);
+                bool sup = false;
+                for (int t = lane; t < nsel; t += 32) sup |= iou_tf(b, sbox[lo + selpos[t]]) > p.iou_thr;   // strict >
+                if (!__any_sync(0xffffffffu, sup)) {
+                    if (lane == 0) selpos[nsel] = (unsigned short)(base + j);
+                    keep |= 1u << j;
+                    nsel++;
+                    __syncwarp();
                 }
-                nsel++;
-                __syncwarp();
+            }
+            if (mine < L) {
+                const unsigned long long k = skey[lo + mine];
+                skey[lo + mine] = ((keep >> lane) & 1u)
+                    ? merge_key(c, __uint_as_float(~(unsigned)((k >> 24) & 0xFFFFFFFFull)), (int)(k & 0xFFFFFFull)) : ~0ull;
             }
         }
+        for (int i = base + lane; i < L; i += 32) skey[lo + i] = ~0ull;       // max_boxes reached: the rest of the class is out
+        __syncwarp();
     }
-    if (lane == 0) p.nwin[img * 256 + c] = nsel;
+    __syncthreads();
+    bitonic_sort_smem<kImgThreads>(skey, n_pad);           // merge keys ascending = score desc, class asc, box asc; ~0 last
+    const float4* boxes = p.boxes + (long long)img * p.N;
+    if (tid == 0 && skey[0] == ~0ull) p.out_valid[img] = 0;
+    for (int k = tid; k < p.max_boxes; k += kImgThreads) {
+        const unsigned long long key = k < n_pad ? skey[k] : ~0ull;
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        float score = 0.f, cls = 0.f;
+        int idx = -1;
+        if (key != ~0ull) {
+            idx = (int)(key & 0xFFFFFFull);
+            cls = (float)((key >> 24) & 0xFFull);
+            score = __uint_as_float(~(unsigned)(key >> 32));
+            b = boxes[idx];
+            b.x = fminf(fmaxf(b.x, 0.f), 1.f); b.y = fminf(fmaxf(b.y, 0.f), 1.f);   // clip_boxes=True
+            b.z = fminf(fmaxf(b.z, 0.f), 1.f); b.w = fminf(fmaxf(b.w, 0.f), 1.f);
+            const unsigned long long nk = (k + 1 < p.max_boxes && k + 1 < n_pad) ? skey[k + 1] : ~0ull;
+            if (nk == ~0ull) p.out_valid[img] = k + 1;      // last valid entry among the first max_boxes
+        }
+        const long long o = (long long)img * p.max_boxes + k;
+        reinterpret_cast<float4*>(p.out_boxes)[o] = b;
+        p.out_scores[o] = score;
+        p.out_classes[o] = cls;
+        p.out_idx[o] = idx;
+    }
 }
 
 // Exact path for images with more than kCandCap candidates (low score thresholds, e.g. mAP export at 0.001; TF's
@@ -375,47 +432,56 @@ __global__ void __launch_bounds__(kOverflowThreads) nms_overflow_kernel(DecodePa
 }
 
 __global__ void __launch_bounds__(kMergeThreads) nms_merge_kernel(NmsParams p) {
-    // k-way merge of the per-class survivor lists (each already score-descending = merge-key ascending): thread c holds the
-    // head of class c; max_boxes rounds of a block-wide min pick the output in order.  (Ranking every survivor against every
-    // class list cost 135 us per batch; the output only needs the first max_boxes of the merged order.)
-    __shared__ unsigned long long wmin[kMergeThreads / 32];
-    __shared__ unsigned long long outkeys[kMaxBoxesCap];
-    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // k-way merge of the per-class survivor lists (each already score-descending = merge-key ascending) by ONE WARP per image:
+    // lane l holds the heads of classes l, l + 32, ... (<= 8 lists per lane at 255 classes); max_boxes rounds of a warp-wide
+    // 64-bit min by shuffles pick the output in order -- no block barriers (the 256-thread version spent 200 of them per image).
+    // kMergeThreads / 32 images per CTA.
+    __shared__ unsigned long long outkeys[kMergeThreads / 32][kMaxBoxesCap];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int img = blockIdx.x * (kMergeThreads / 32) + w;
+    if (img >= p.merge_batch || p.cand_count[img] <= kCandCap) return;     // nms_image_kernel did this image
     const unsigned long long kNone = ~0ull;
-    const unsigned long long* list = p.win_keys + ((long long)img * p.nc + tid) * p.max_boxes;
-    const int cnt = tid < p.nc ? p.nwin[img * 256 + tid] : 0;
-    int cur = 0;
-    unsigned long long head = cnt > 0 ? list[0] : kNone;
-    unsigned long long nxt = cnt > 1 ? list[1] : kNone;       // one element of lookahead hides the global-load latency
+    constexpr int PER = 8;                                    // ceil(255 / 32)
+    unsigned long long head[PER], nxt[PER];
+    int cur[PER], cnt[PER];
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const int c = lane + 32 * i;
+        cnt[i] = c < p.nc ? p.nwin[img * 256 + c] : 0;
+        const unsigned long long* list = p.win_keys + ((long long)img * p.nc + (c < p.nc ? c : 0)) * p.max_boxes;
+        cur[i] = 0;
+        head[i] = cnt[i] > 0 ? list[0] : kNone;
+        nxt[i] = cnt[i] > 1 ? list[1] : kNone;             // one element of lookahead hides the global-load latency
+    }
     int nvalid = 0;
     for (int k = 0; k < p.max_boxes; k++) {
-        unsigned long long m = head;
+        unsigned long long m = head[0];
+#pragma unroll
+        for (int i = 1; i < PER; i++) m = head[i] < m ? head[i] : m;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) { const unsigned long long o = __shfl_xor_sync(0xffffffffu, m, d); m = o < m ? o : m; }
-        if (lane == 0) wmin[warp] = m;
-        __syncthreads();
-        unsigned long long best = wmin[0];
-#pragma unroll
-        for (int w = 1; w < kMergeThreads / 32; w++) best = wmin[w] < best ? wmin[w] : best;
-        __syncthreads();
-        if (best == kNone) break;                             // block-uniform: every list is exhausted
-        if (tid == 0) outkeys[k] = best;
+        if (m == kNone) break;                                // warp-uniform: every list is exhausted
+        if (lane == 0) outkeys[w][k] = m;
         nvalid = k + 1;
-        if (head == best) {                                   // keys are unique: exactly one owner
-            cur++;
-            head = nxt;
-            nxt = cur + 1 < cnt ? list[cur + 1] : kNone;
-        }
+#pragma unroll
+        for (int i = 0; i < PER; i++)
+            if (head[i] == m) {                               // keys are unique: exactly one owner
+                const int c = lane + 32 * i;
+                const unsigned long long* list = p.win_keys + ((long long)img * p.nc + c) * p.max_boxes;
+                cur[i]++;
+                head[i] = nxt[i];
+                nxt[i] = cur[i] + 1 < cnt[i] ? list[cur[i] + 1] : kNone;
+            }
     }
-    __syncthreads();
+    __syncwarp();
     const float4* boxes = p.boxes + (long long)img * p.N;
-    if (tid == 0) p.out_valid[img] = nvalid;
-    for (int k = tid; k < p.max_boxes; k += kMergeThreads) {
+    if (lane == 0) p.out_valid[img] = nvalid;
+    for (int k = lane; k < p.max_boxes; k += 32) {
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
         float score = 0.f, cls = 0.f;
         int idx = -1;
         if (k < nvalid) {
-            const unsigned long long key = outkeys[k];
+            const unsigned long long key = outkeys[w][k];
             idx = (int)(key & 0xFFFFFFull);
             cls = (float)((key >> 24) & 0xFFull);
             score = __uint_as_float(~(unsigned)(key >> 32));

@@ -459,7 +459,7 @@ __global__ void l2_flush_kernel(float4* buf, long long n, float v) {
 }
 
 // packed user heads (B,g,g,C) -> padded-flat fp32 head buffer (ld = ld_out)
-__global__ void scatter_head_kernel(const float* src, float* dst, int N, int g, int C, int ld_out) {
+__global__ void scatter_head_kernel(const float* src, float* dst, int N, int g, int C, int ld_out, float* obj, long long obj_rows, int nc5) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long total = (long long)N * g * g * C;
     if (i >= total) return;
@@ -468,7 +468,9 @@ __global__ void scatter_head_kernel(const float* src, float* dst, int N, int g, 
     int w = (int)(t % g); t /= g;
     int h = (int)(t % g);
     int n = (int)(t / g);
-    dst[(((long long)n * (g + 2) + h + 1) * (g + 2) + w + 1) * ld_out + c] = src[i];
+    const long long prow = ((long long)n * (g + 2) + h + 1) * (g + 2) + w + 1;
+    dst[prow * ld_out + c] = src[i];
+    if (obj && c % nc5 == 4) obj[(c / nc5) * obj_rows + prow] = src[i];      // compact objectness copy (decode_nms.cuh DecodeParams::obj)
 }
 
 // padded-flat (any T) view -> packed NHWC float (debug / y4_forward_heads)

@@ -101,9 +101,12 @@ struct y4_engine {
     int head_ld = 0;
     int head_buf[3] = {-1, -1, -1};
     float* d_user_heads[3] = {nullptr, nullptr, nullptr};
+    float* d_obj[3] = {nullptr, nullptr, nullptr};     // compact objectness logits [3][rows] per scale, written by the tcgen05 head convs
+    long long obj_rows[3] = {0, 0, 0};
+    bool obj_valid = false;                            // all three head convs run a tcgen05 plan that writes d_obj
     unsigned long long* d_cand_keys = nullptr;
-    unsigned long long *d_bucket_keys = nullptr, *d_sorted_keys = nullptr, *d_win_keys = nullptr;   // NMS workspace (decode_nms.cuh)
-    int *d_seg_start = nullptr, *d_nwin = nullptr;
+    unsigned long long* d_win_keys = nullptr;          // NMS workspace of the overflow path (decode_nms.cuh)
+    int* d_nwin = nullptr;
     int* d_cand_count = nullptr;
     float4* d_boxes = nullptr;
     float* d_out_boxes = nullptr; float* d_out_scores = nullptr; float* d_out_classes = nullptr;
@@ -496,6 +499,7 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
     for (int i = 0; i < 3; i++) {
         if (user_heads) { d.head[i] = user_heads[i]; d.ld[i] = 3 * (5 + nc); d.padded[i] = 0; }
         else { d.head[i] = (const float*)e->bufs[e->head_buf[i]].ptr; d.ld[i] = e->head_ld; d.padded[i] = 1; }
+        d.obj[i] = (!user_heads && e->obj_valid) ? e->d_obj[i] : nullptr; d.obj_rows[i] = e->obj_rows[i];
         d.g[i] = e->g[i]; d.stride[i] = (float)e->cfg.strides[i];
         d.xyscale[i] = (float)e->cfg.xyscale[i];
         d.xyoff[i] = (float)(0.5 * (e->cfg.xyscale[i] - 1.0));
@@ -507,21 +511,23 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
     d.nc = nc; d.C = 5 + nc; d.N = e->N; d.batch = batch; d.img_size = (float)e->cfg.img_size; d.score_thr = score_thr;
     d.cand_keys = e->d_cand_keys; d.cand_count = e->d_cand_count; d.boxes = e->d_boxes;
     CUDA_TRY(e, cudaMemsetAsync(e->d_cand_count, 0, sizeof(int) * batch, e->stream));
-    unsigned blocks = (unsigned)(((long long)batch * e->N + 255) / 256);       // one thread per box
-    decode_filter_kernel<<<blocks, 256, 0, e->stream>>>(d);
+    decode_filter_kernel<<<dim3((unsigned)((e->N + kFilterThreads - 1) / kFilterThreads), (unsigned)batch), kFilterThreads, 0, e->stream>>>(d);
     NmsParams n{};
     n.cand_keys = e->d_cand_keys; n.cand_count = e->d_cand_count; n.boxes = e->d_boxes;
     n.N = e->N; n.nc = nc; n.max_boxes = e->cfg.max_boxes; n.iou_thr = iou_thr;
     n.out_boxes = e->d_out_boxes; n.out_scores = e->d_out_scores; n.out_classes = e->d_out_classes;
     n.out_valid = e->d_out_valid; n.out_idx = e->d_out_idx;
-    n.bucket_keys = e->d_bucket_keys; n.sorted_keys = e->d_sorted_keys; n.seg_start = e->d_seg_start;
     n.win_keys = e->d_win_keys; n.nwin = e->d_nwin;
-    nms_bucket_kernel<<<batch, kBucketThreads, 0, e->stream>>>(n);
-    nms_class_kernel<<<batch * nc, kClassThreads, 0, e->stream>>>(n);
+    n.merge_batch = batch;
+    {
+        static DeviceOnce once;                                        // the attribute is per device
+        if (once.first_use()) cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kImgSmemBytes);
+    }
+    nms_image_kernel<<<batch, kImgThreads, kImgSmemBytes, e->stream>>>(n);
     // images with more than kCandCap candidates (none in the usual case: the CTAs return at once) are redone exactly, from the heads
     nms_overflow_kernel<<<batch * nc, kOverflowThreads, sizeof(unsigned) * ((e->N + 31) / 32), e->stream>>>(d, n);
-    nms_merge_kernel<<<batch, kMergeThreads, 0, e->stream>>>(n);
-    e->launches += 5;
+    nms_merge_kernel<<<(batch + kMergeThreads / 32 - 1) / (kMergeThreads / 32), kMergeThreads, 0, e->stream>>>(n);
+    e->launches += 4;
     CUDA_TRY(e, cudaGetLastError());
     return Y4_OK;
 }
@@ -709,14 +715,15 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             CREATE_TRY(cudaMemset(c.d_wscale, 0, sizeof(float) * c.cout_pad));
         }
     }
-    for (int i = 0; i < 3; i++)
+    for (int i = 0; i < 3; i++) {
         CREATE_TRY(cudaMalloc(&e->d_user_heads[i], sizeof(float) * B * e->g[i] * e->g[i] * 3 * (5 + cfg->num_classes)));
+        e->obj_rows[i] = (long long)B * (e->g[i] + 2) * (e->g[i] + 2);
+        CREATE_TRY(cudaMalloc(&e->d_obj[i], sizeof(float) * 3 * e->obj_rows[i]));
+        CREATE_TRY(cudaMemset(e->d_obj[i], 0, sizeof(float) * 3 * e->obj_rows[i]));
+    }
     CREATE_TRY(cudaMalloc(&e->d_cand_keys, sizeof(unsigned long long) * kCandCap * B));
     CREATE_TRY(cudaMalloc(&e->d_cand_count, sizeof(int) * B));
-    CREATE_TRY(cudaMalloc(&e->d_bucket_keys, sizeof(unsigned long long) * kCandCap * B));
-    CREATE_TRY(cudaMalloc(&e->d_sorted_keys, sizeof(unsigned long long) * kCandCap * B));
     CREATE_TRY(cudaMalloc(&e->d_win_keys, sizeof(unsigned long long) * (size_t)cfg->num_classes * mb * B));
-    CREATE_TRY(cudaMalloc(&e->d_seg_start, sizeof(int) * 257 * B));
     CREATE_TRY(cudaMalloc(&e->d_nwin, sizeof(int) * 256 * B));
     CREATE_TRY(cudaMalloc(&e->d_boxes, sizeof(float4) * e->N * B));
     CREATE_TRY(cudaMemset(e->d_boxes, 0, sizeof(float4) * e->N * B));
@@ -739,6 +746,9 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             d.out = ob.ptr; d.out_ld = ob.C; d.out_choff = c.out.choff; d.out_f32 = c.out_f32; d.upsample = c.upsample;
             if (c.has_res) { const Buf& rb = e->bufs[c.res.buf]; d.res = rb.ptr; d.res_ld = rb.C; d.res_choff = c.res.choff; }
             d.w16 = c.d_w16; d.bias = c.d_bias; d.w16_pair = split ? nullptr : c.d_w16_pair;
+            if (c.out_f32)
+                for (int hi = 0; hi < 3; hi++)
+                    if (c.out.buf == e->head_buf[hi]) { d.obj_out = e->d_obj[hi]; d.obj_c0 = 4; d.obj_stride = 5 + cfg->num_classes; d.obj_rows = e->obj_rows[hi]; }
             if (c.fused_a >= 0) { const Buf& ob2 = e->bufs[c.out2.buf]; d.out2 = ob2.ptr; d.out2_ld = ob2.C; d.out2_choff = c.out2.choff; d.split_col = c.cout / 2; }
             if (split) {
                 d.split = 1; d.w16_lo = c.d_w16_lo; d.wscale = c.d_wscale; d.out_lo = ob.ptr_lo;
@@ -948,6 +958,11 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         }
         // autotune launches wrote act(bias=0)=0-ish garbage into interiors only; halos were never touched.
     }
+    {
+        int nh = 0;
+        for (auto& c : e->convs) nh += (c.out_f32 && (c.kind == 1 || c.kind == 2)) ? 1 : 0;
+        e->obj_valid = nh == 3;
+    }
     CREATE_TRY(cudaDeviceSynchronize());
     *out = e;
     return Y4_OK;
@@ -965,9 +980,9 @@ void y4_destroy(y4_engine* e) {
     for (int i = 0; i < 2; i++) { if (e->ev_h2d[i]) cudaEventDestroy(e->ev_h2d[i]); if (e->ev_done[i]) cudaEventDestroy(e->ev_done[i]); if (e->stage[i]) cudaFreeHost(e->stage[i]); }
     for (int i = 0; i < 2; i++) { cudaFree(e->d_u8[i]); cudaFree(e->d_pre[i]); if (e->h_pre[i]) cudaFreeHost(e->h_pre[i]); }
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-    for (int i = 0; i < 3; i++) cudaFree(e->d_user_heads[i]);
+    for (int i = 0; i < 3; i++) { cudaFree(e->d_user_heads[i]); cudaFree(e->d_obj[i]); }
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
-    cudaFree(e->d_bucket_keys); cudaFree(e->d_sorted_keys); cudaFree(e->d_win_keys); cudaFree(e->d_seg_start); cudaFree(e->d_nwin);
+    cudaFree(e->d_win_keys); cudaFree(e->d_nwin);
     cudaFree(e->d_out_boxes); cudaFree(e->d_out_scores); cudaFree(e->d_out_classes);
     cudaFree(e->d_out_valid); cudaFree(e->d_out_idx);
     cudaFree(e->d_flush); cudaFree(e->d_gather);
@@ -1116,7 +1131,7 @@ int y4_upload_heads(y4_engine* e, const float* hs, const float* hm, const float*
         long long total = (long long)batch * e->g[i] * e->g[i] * C;
         CUDA_TRY(e, cudaMemcpyAsync(e->d_user_heads[i], ins[i], total * sizeof(float), cudaMemcpyHostToDevice, e->stream));
         scatter_head_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(
-            e->d_user_heads[i], (float*)e->bufs[e->head_buf[i]].ptr, batch, e->g[i], C, e->head_ld);
+            e->d_user_heads[i], (float*)e->bufs[e->head_buf[i]].ptr, batch, e->g[i], C, e->head_ld, e->d_obj[i], e->obj_rows[i], 5 + e->cfg.num_classes);
         e->launches++;
     }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
