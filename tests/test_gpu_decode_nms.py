@@ -97,22 +97,25 @@ def test_no_candidate_limit():
     eng.close()
 
 
-def test_long_class_segment():
-    """More than 1024 candidates of ONE class in an image that still fits the fast path (arg-max rounds instead of the
-    shared-memory rank sort in nms_class_kernel)."""
+@pytest.mark.parametrize('n_hot', [3000, 600, 90])
+def test_long_class_segment(n_hot):
+    """Many candidates of ONE class in an image that still fits the fast path.  nms_image_kernel has three regimes per class
+    segment: <= 32 candidates (lane-parallel pair tests inside one warp), up to 704 (pairwise bit matrix built by the whole
+    CTA, n_hot = 90 and 600), longer (sequential scan, n_hot = 3000); heavy overlap makes every regime suppress."""
     import y4b200
     import y4_oracle as O
     S = 416
     heads = O.synth_heads(seed=12, batch=1, img_size=S, n_clusters=20)
     rng = np.random.default_rng(0)
     h = heads[0].reshape(1, S // 8, S // 8, 3, 85)
-    pick = rng.choice(h.shape[1] * h.shape[2] * 3, 3000, replace=False)
+    pick = rng.choice(h.shape[1] * h.shape[2] * 3, n_hot, replace=False)
     r, c, a = np.unravel_index(pick, (h.shape[1], h.shape[2], 3))
-    h[0, r, c, a, 4] = rng.uniform(1, 6, 3000).astype(np.float32)
-    h[0, r, c, a, 5 + 7] = rng.uniform(1, 6, 3000).astype(np.float32)
+    h[0, r, c, a, 4] = rng.uniform(1, 6, n_hot).astype(np.float32)
+    h[0, r, c, a, 5 + 7] = rng.uniform(1, 6, n_hot).astype(np.float32)
+    h[0, r, c, a, 2:4] += 1.5                                  # larger boxes: plenty of pairs above the IoU threshold
     boxes, scores = O.decode_heads(heads, S)
     per_class = (scores[0] > np.float32(0.3)).sum(axis=0)
-    assert per_class[7] > 1024 and per_class.sum() <= 8192, (per_class[7], per_class.sum())
+    assert per_class[7] > 0.8 * n_hot and per_class.sum() <= 8192, (per_class[7], per_class.sum())
     eng = y4b200.Engine(img_size=S, max_batch=1)
-    _check(eng.decode_nms(heads, with_indices=True), O.combined_nms(boxes, scores), 'long_segment')
+    _check(eng.decode_nms(heads, with_indices=True), O.combined_nms(boxes, scores), f'long_segment_{n_hot}')
     eng.close()

@@ -107,6 +107,8 @@ struct y4_engine {
     unsigned long long* d_cand_keys = nullptr;
     unsigned long long* d_win_keys = nullptr;          // NMS workspace of the overflow path (decode_nms.cuh)
     int* d_nwin = nullptr;
+    unsigned long long* d_part_keys = nullptr;         // nms_image_kernel: per-part survivor lists, [B][kMaxParts][kMaxBoxesCap]
+    int* d_ticket = nullptr;                           // [B], zero between launches
     int* d_cand_count = nullptr;
     float4* d_boxes = nullptr;
     float* d_out_boxes = nullptr; float* d_out_scores = nullptr; float* d_out_classes = nullptr;
@@ -509,6 +511,12 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
     d.cell_off[3] = cells;
     for (int i = 0; i < 18; i++) d.anchors[i] = e->cfg.anchors[i];
     d.nc = nc; d.C = 5 + nc; d.N = e->N; d.batch = batch; d.img_size = (float)e->cfg.img_size; d.score_thr = score_thr;
+    {   // logits below this cannot pass the threshold (DecodeParams::logit_lo)
+        const double t = (double)score_thr;
+        if (!(t > 0.0)) d.logit_lo = -INFINITY;
+        else if (!(t < 1.0)) d.logit_lo = INFINITY;
+        else { const double lt = log(t / (1.0 - t)); d.logit_lo = (float)(lt - 1e-3 - 1e-3 * fabs(lt)); }
+    }
     d.cand_keys = e->d_cand_keys; d.cand_count = e->d_cand_count; d.boxes = e->d_boxes;
     CUDA_TRY(e, cudaMemsetAsync(e->d_cand_count, 0, sizeof(int) * batch, e->stream));
     decode_filter_kernel<<<dim3((unsigned)((e->N + kFilterThreads - 1) / kFilterThreads), (unsigned)batch), kFilterThreads, 0, e->stream>>>(d);
@@ -517,13 +525,16 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
     n.N = e->N; n.nc = nc; n.max_boxes = e->cfg.max_boxes; n.iou_thr = iou_thr;
     n.out_boxes = e->d_out_boxes; n.out_scores = e->d_out_scores; n.out_classes = e->d_out_classes;
     n.out_valid = e->d_out_valid; n.out_idx = e->d_out_idx;
-    n.win_keys = e->d_win_keys; n.nwin = e->d_nwin;
+    n.win_keys = e->d_win_keys; n.nwin = e->d_nwin; n.part_keys = e->d_part_keys; n.ticket = e->d_ticket;
     n.merge_batch = batch;
     {
         static DeviceOnce once;                                        // the attribute is per device
         if (once.first_use()) cudaFuncSetAttribute(nms_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kImgSmemBytes);
     }
-    nms_image_kernel<<<batch, kImgThreads, kImgSmemBytes, e->stream>>>(n);
+    int parts = sm_count() / batch;                                    // CTAs per image: all of them resident at once
+    parts = parts < 1 ? 1 : (parts > kMaxParts ? kMaxParts : parts);
+    if (parts > nc) parts = nc;
+    nms_image_kernel<<<dim3((unsigned)parts, (unsigned)batch), kImgThreads, kImgSmemBytes, e->stream>>>(n);
     // images with more than kCandCap candidates (none in the usual case: the CTAs return at once) are redone exactly, from the heads
     nms_overflow_kernel<<<batch * nc, kOverflowThreads, sizeof(unsigned) * ((e->N + 31) / 32), e->stream>>>(d, n);
     nms_merge_kernel<<<(batch + kMergeThreads / 32 - 1) / (kMergeThreads / 32), kMergeThreads, 0, e->stream>>>(n);
@@ -725,6 +736,9 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
     CREATE_TRY(cudaMalloc(&e->d_cand_count, sizeof(int) * B));
     CREATE_TRY(cudaMalloc(&e->d_win_keys, sizeof(unsigned long long) * (size_t)cfg->num_classes * mb * B));
     CREATE_TRY(cudaMalloc(&e->d_nwin, sizeof(int) * 256 * B));
+    CREATE_TRY(cudaMalloc(&e->d_part_keys, sizeof(unsigned long long) * kMaxParts * kMaxBoxesCap * B));
+    CREATE_TRY(cudaMalloc(&e->d_ticket, sizeof(int) * B));
+    CREATE_TRY(cudaMemset(e->d_ticket, 0, sizeof(int) * B));
     CREATE_TRY(cudaMalloc(&e->d_boxes, sizeof(float4) * e->N * B));
     CREATE_TRY(cudaMemset(e->d_boxes, 0, sizeof(float4) * e->N * B));
     CREATE_TRY(cudaMalloc(&e->d_out_boxes, sizeof(float) * 4 * mb * B));
@@ -821,7 +835,9 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         // (and therefore across GPUs, whatever each one picks).
         struct Cand { int bn, kb, patch, group, epi, nepi, bres, gw, cta2, lean, pairx; };
         std::vector<Cand> cands;
-        const bool allow_patch = getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '1';    // A-patch plans: correct, never the fastest in context on B200
+        // single-CTA A-patch plans: since the warp-uniform issue loops the per-kernel-row patch wins on conv 5 (3x3 32->64 at 304^2:
+        // 0.346 -> 0.309 ms, three 130-row loads instead of nine 128-row ones); Y4_PATCH=0 removes them from the candidate list
+        const bool allow_patch = !(getenv("Y4_PATCH") && getenv("Y4_PATCH")[0] == '0');
         const bool allow_bres = !(getenv("Y4_BRES") && getenv("Y4_BRES")[0] == '0');
         const int epi_mode = getenv("Y4_EPI") ? atoi(getenv("Y4_EPI")) : 1;     // 0 never, 1 autotune, 2 wherever eligible
         const int nepi_mode = getenv("Y4_NEPI") ? atoi(getenv("Y4_NEPI")) : 0;  // 4 / 8: only that many epilogue warps
@@ -982,7 +998,7 @@ void y4_destroy(y4_engine* e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 3; i++) { cudaFree(e->d_user_heads[i]); cudaFree(e->d_obj[i]); }
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
-    cudaFree(e->d_win_keys); cudaFree(e->d_nwin);
+    cudaFree(e->d_win_keys); cudaFree(e->d_nwin); cudaFree(e->d_part_keys); cudaFree(e->d_ticket);
     cudaFree(e->d_out_boxes); cudaFree(e->d_out_scores); cudaFree(e->d_out_classes);
     cudaFree(e->d_out_valid); cudaFree(e->d_out_idx);
     cudaFree(e->d_flush); cudaFree(e->d_gather);
