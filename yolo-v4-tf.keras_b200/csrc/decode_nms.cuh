@@ -195,6 +195,14 @@ __device__ __forceinline__ float iou_tf(const float4 a, const float4 b) {
     return __fdiv_rn(inter, __fsub_rn(__fadd_rn(area_a, area_b), inter));
 }
 
+// Necessary condition for iou_tf(a, b) > thr when thr >= 0: a strictly positive overlap in both axes (same min / max re-ordering;
+// a rounded difference is positive exactly when the true one is).
+__device__ __forceinline__ bool boxes_intersect(const float4 a, const float4 b) {
+    const float iy0 = fmaxf(fminf(a.x, a.z), fminf(b.x, b.z)), iy1 = fminf(fmaxf(a.x, a.z), fmaxf(b.x, b.z));
+    const float ix0 = fmaxf(fminf(a.y, a.w), fminf(b.y, b.w)), ix1 = fminf(fmaxf(a.y, a.w), fmaxf(b.y, b.w));
+    return iy1 > iy0 && ix1 > ix0;
+}
+
 struct NmsParams {
     const unsigned long long* cand_keys;   // [batch][kCandCap]   decode output, unordered
     const int* cand_count;                 // [batch]
@@ -284,7 +292,8 @@ __global__ void __launch_bounds__(kImgThreads, 1) nms_image_kernel(NmsParams p) 
     float4* sbox = reinterpret_cast<float4*>(nms_smem + (size_t)kCandCap * 8);                  // [cnt] boxes in sorted order
     unsigned short* selpos_all = reinterpret_cast<unsigned short*>(nms_smem + (size_t)kCandCap * 24);
     __shared__ int seg_lo[256], seg_hi[256];
-    __shared__ unsigned s_sup[kImgThreads / 32][32];
+    __shared__ unsigned s_sup[kImgThreads / 32][128];       // per warp: 64 candidates x 64-bit suppression mask
+    __shared__ unsigned short s_pq[kImgThreads / 32][64];        // per warp: queue of intersecting pairs (i << 8 | j)
     __shared__ unsigned char long_list[256];
     __shared__ int next_class, s_cnt, s_last, n_long;
     const int img = blockIdx.y, part = blockIdx.x, K = gridDim.x;
@@ -326,6 +335,7 @@ __global__ void __launch_bounds__(kImgThreads, 1) nms_image_kernel(NmsParams p) 
     // ---- 2. TF's greedy scan per class, one warp per class, classes handed out dynamically
     unsigned short* selpos = selpos_all;                    // sequential fallback (warp 0 only)
     unsigned* sup = s_sup[warp];
+    unsigned short* pq = s_pq[warp];
     while (true) {
         int c = 0;
         if (lane == 0) c = atomicAdd(&next_class, K);
@@ -333,43 +343,68 @@ __global__ void __launch_bounds__(kImgThreads, 1) nms_image_kernel(NmsParams p) 
         if (c >= p.nc) break;
         const int lo = seg_lo[c], L = seg_hi[c] - lo;
         if (L == 0) continue;
-        if (L > 32) {                                       // long segment: done by the whole CTA below
+        if (L > 64) {                                       // long segment: done by the whole CTA below
             if (lane == 0) long_list[atomicAdd(&n_long, 1)] = (unsigned char)c;
             continue;
         }
-        // the usual case.  Candidate i is dropped iff an earlier SELECTED candidate j has iou > thr: the L(L-1)/2 iou tests do not
-        // depend on the selection, so they run one pair per lane (L = 13: 3 warp passes instead of 13 sequential ones), leaving a
-        // bit mask per candidate; the sequential part is then three integer instructions per candidate.
-        sup[lane] = 0u;
+        // The usual case, one warp per class.  Candidate i is dropped iff an earlier SELECTED candidate j has iou > thr.  The pair
+        // tests do not depend on the selection, so they run lane-parallel and leave a 64-bit mask per candidate
+        // (sup[i] = { j < i : iou(i, j) > thr }); the sequential part is then a few integer instructions per candidate.
+        //   pass 1: for every i, lanes j < i test whether the two boxes intersect at all (a dozen instructions; a pair that does
+        //           not has iou = 0) and queue the pairs that do;
+        //   pass 2: the exact TF iou (with its IEEE division) runs on full warps of queued pairs only -- in clustered detections
+        //           that is ~10 % of the pairs.
+        sup[lane] = 0u; sup[lane + 32] = 0u; sup[lane + 64] = 0u; sup[lane + 96] = 0u;
+        const float4 bj0 = lane < L ? sbox[lo + lane] : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 bj1 = lane + 32 < L ? sbox[lo + lane + 32] : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
-        const int P = L * (L - 1) / 2;
-        for (int p0 = 0; p0 < P; p0 += 32) {
-            const int pp = p0 + lane;
-            if (pp < P) {
-                int i = (int)((1.f + sqrtf(1.f + 8.f * (float)pp)) * 0.5f);     // pair index -> (i, j), j < i
-                while (i * (i - 1) / 2 > pp) i--;
-                while ((i + 1) * i / 2 <= pp) i++;
-                const int j = pp - i * (i - 1) / 2;
-                if (iou_tf(sbox[lo + i], sbox[lo + j]) > p.iou_thr) atomicOr(&sup[i], 1u << j);   // strict >
+        int nq = 0;
+        auto drain = [&](int first, int n) {               // exact test of queued pairs [first, first + n), n <= 32
+            if (lane < n) {
+                const unsigned pr = pq[first + lane];
+                const int i = (int)(pr >> 8), j = (int)(pr & 0xFFu);
+                if (iou_tf(sbox[lo + i], sbox[lo + j]) > p.iou_thr) atomicOr(&sup[2 * i + (j >> 5)], 1u << (j & 31));   // strict >
+            }
+        };
+        const bool all_pairs = !(p.iou_thr >= 0.f);         // a negative (or NaN) threshold: iou = 0 decides too, nothing may be skipped
+        for (int i = 1; i < L; i++) {
+            const float4 bi = sbox[lo + i];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (32 * h >= i) break;                     // warp-uniform
+                const int j = 32 * h + lane;
+                const float4 bj = h ? bj1 : bj0;
+                const bool ok = j < i && (all_pairs || boxes_intersect(bi, bj));
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) pq[nq + __popc(m & lt)] = (unsigned short)((i << 8) | j);
+                nq += __popc(m);
+                __syncwarp();
+                if (nq >= 32) { nq -= 32; drain(nq, 32); __syncwarp(); }
             }
         }
+        drain(0, nq);
         __syncwarp();
-        const unsigned S = sup[lane];
-        unsigned selmask = 0u;
+        const unsigned S0a = sup[2 * lane], S0b = sup[2 * lane + 1], S1a = sup[2 * lane + 64], S1b = sup[2 * lane + 65];
+        unsigned sel0 = 0u, sel1 = 0u;
         int nsel = 0;
         for (int j = 0; j < L && nsel < p.max_boxes; j++) {
-            const unsigned Sj = __shfl_sync(0xffffffffu, S, j);
-            if ((Sj & selmask) == 0u) { selmask |= 1u << j; nsel++; }
+            const unsigned sa = __shfl_sync(0xffffffffu, j < 32 ? S0a : S1a, j & 31);
+            const unsigned sb = __shfl_sync(0xffffffffu, j < 32 ? S0b : S1b, j & 31);
+            if (((sa & sel0) | (sb & sel1)) == 0u) { if (j < 32) sel0 |= 1u << j; else sel1 |= 1u << (j - 32); nsel++; }
         }
-        if (lane < L) {
-            const unsigned long long k = skey[lo + lane];
-            skey[lo + lane] = ((selmask >> lane) & 1u)
-                ? merge_key(c, __uint_as_float(~(unsigned)((k >> 24) & 0xFFFFFFFFull)), (int)(k & 0xFFFFFFull)) : ~0ull;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int i = 32 * h + lane;
+            if (i < L) {
+                const unsigned long long k = skey[lo + i];
+                skey[lo + i] = (((h ? sel1 : sel0) >> lane) & 1u)
+                    ? merge_key(c, __uint_as_float(~(unsigned)((k >> 24) & 0xFFFFFFFFull)), (int)(k & 0xFFFFFFull)) : ~0ull;
+            }
         }
         __syncwarp();
     }
     __syncthreads();
-    // ---- 2b. segments of more than 32 candidates, one after the other, by the whole CTA: all threads fill the bit matrix
+    // ---- 2b. segments of more than 64 candidates, one after the other, by the whole CTA: all threads fill the bit matrix
     // M[i] = { j < i : iou(i, j) > thr } (L^2 / 2 tests, 1024 at a time), then warp 0 walks the candidates in order with the
     // selected set as a bit vector across its lanes (one shared-memory read + one vote per candidate).  The matrix lives in the
     // unused upper half of the box array (64 KB: segments up to 704 candidates while this part holds <= kCandCap / 2 keys); longer
@@ -385,7 +420,8 @@ __global__ void __launch_bounds__(kImgThreads, 1) nms_image_kernel(NmsParams p) 
             __syncthreads();
             for (int pp = tid; pp < L * L; pp += kImgThreads) {
                 const int i = pp / L, j = pp - i * L;
-                if (j < i && iou_tf(sbox[lo + i], sbox[lo + j]) > p.iou_thr) atomicOr(&M[i * W + (j >> 5)], 1u << (j & 31));   // strict >
+                if (j < i && (!(p.iou_thr >= 0.f) || boxes_intersect(sbox[lo + i], sbox[lo + j])) && iou_tf(sbox[lo + i], sbox[lo + j]) > p.iou_thr)
+                    atomicOr(&M[i * W + (j >> 5)], 1u << (j & 31));   // strict >
             }
             __syncthreads();
             if (warp == 0) {
