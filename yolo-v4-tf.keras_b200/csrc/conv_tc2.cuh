@@ -636,6 +636,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
                 if (!encode_map(&p.tmA[ph * 2 + pw], b, 4, dims, str, box4, 128, err)) return -1;
             }
     }
+    const bool deep_b = patch && group >= 2;                   // patch mode, `group` 2: as many B stages as fit beside three patches
     if (patch || group < 1) group = 1;
     if (group > p.num_kb) group = p.num_kb;
     p.group = group;
@@ -674,10 +675,25 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
         if (!encode_map(&p.tmA[1], in_base, 2, dims, str, box2, 128, err)) return -1;
         stage_bytes = (size_t)(bn / 2) * 64 * 2;
         S = 6;                                                         // B stages: a half B tile is small and re-fetched per tap
+        if (deep_b) {
+            // a B stage feeds four MMAs (256 tensor cycles at N = 128): six stages cover ~1,500 cycles of L2 latency, which is
+            // borderline under load.  Deep variant: three patch slots (two if three do not fit), the rest of the budget as B stages.
+            int best_s = 0, best_ps = 0;
+            for (int ps = 3; ps >= 2 && !best_s; ps--) {
+                if (budget < fixed + 64 + (size_t)ps * (size_t)p.patch_bytes) continue;
+                int s2 = (int)((budget - fixed - 64 - (size_t)ps * (size_t)p.patch_bytes) / stage_bytes);
+                if (s2 > 12) s2 = 12;
+                if (s2 > 6) { best_s = s2; best_ps = ps; }
+            }
+            if (!best_s) return 0;                                     // nothing deeper than the default fits: no new plan
+            S = best_s;
+            p.patch_slots = best_ps;
+        } else {
         const size_t bpart = (size_t)S * stage_bytes;
         if (budget < fixed + bpart + 2 * (size_t)p.patch_bytes) return 0;
         int PS = (int)((budget - fixed - bpart) / (size_t)p.patch_bytes);
         p.patch_slots = PS > 4 ? 4 : PS;
+        }
         patch_total = (size_t)p.patch_slots * (size_t)p.patch_bytes;
     } else {
         S = budget > fixed ? (int)((budget - fixed) / stage_bytes) : 0;

@@ -860,7 +860,12 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             if (allow_cta2 && !(getenv("Y4_PATCH2") && getenv("Y4_PATCH2")[0] == '0'))   // CTA pair + A-patch reuse (3x3 stride 1): cuts the L2 -> smem traffic
                 for (int bn : {64, 128, 256})
                     for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}})
-                        cands.push_back({bn, 224, 1, 1, 1, ep.first, 0, ep.second, 1});
+                        for (int g : {1, 2}) {
+                            // g = 2: deep B ring (tc_plan2: up to 12 weight stages beside three patches).  Measured: no gain on any layer
+                            // (the six-stage ring already covers the L2 latency), so it stays out of the default list: Y4_DEEPB=1
+                            if (g == 2 && !(getenv("Y4_DEEPB") && getenv("Y4_DEEPB")[0] == '1')) continue;
+                            cands.push_back({bn, 224, 1, g, 1, ep.first, 0, ep.second, 1});
+                        }
             for (int bres = 0; bres <= (allow_bres ? 1 : 0); bres++)            // lean 4-warp epilogue, four CTAs per SM (64-wide tiles)
                 for (int gw : {32, 64})
                     for (int kb : {56, 75}) cands.push_back({64, kb, 0, 1, 1, 4, bres, gw, 0, 1});
