@@ -23,6 +23,8 @@ FAMILIES = {
     'cta_pair_bn256_slab8': '256,224,0,2,1,8,0,32,1,0,0',
     'cta_pair_bn128_gw64': '128,224,0,3,1,4,0,64,1,0,0',
     'cta_pair_patch_bn128': '128,224,1,1,1,8,0,32,1,0,0',
+    'cta_pair_bn128_16_epilogue_warps': '128,224,0,1,1,16,0,32,1,0,0',
+    'cta_pair_patch_bn256_16_epilogue_warps': '256,224,1,1,1,16,0,32,1,0,0',
     'cta_pair_patch_bn256': '256,224,1,1,1,4,0,32,1,0,0',
     'bn64_per_thread_stores': '64,112,0,1,0,4,0,32,0,0,0',
     'lean_resident_w_gw64': '64,75,0,1,1,4,1,64,0,1,0',

@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
             };
             auto release_now = [&]() { tc_fence_before(); if (lane == 0) mbar_arrive_leader(bar_tempty + 8u * as); };
             auto release_acc = [&]() { if (!chain) release_now(); };      // chain fusion: the stage is handed back after the second epilogue
-            if constexpr (NEPI == 8) {
+            if constexpr (NEPI >= 8) {
 #pragma unroll 1
                 for (int k = set; k < NCH; k += NSETS) {
                     tmem_ld32_issue(tacc + (uint32_t)(32 * k), va);
@@ -541,7 +541,12 @@ inline int tc2_launch(const TcConvPlan& pl_in, int batch, cudaStream_t st) {
     const int nclusters = pl.p.num_tiles < max_clusters ? pl.p.num_tiles : max_clusters;
     dim3 grid((unsigned)(2 * nclusters));
     cudaError_t e = cudaErrorInvalidValue;
-    if (pl.nepi == 8) {
+    if (pl.nepi == 16) {
+        switch (pl.tile_n) {
+            case 128: e = launch_tc2<128, 16>(pl, grid, st); break;
+            case 256: e = launch_tc2<256, 16>(pl, grid, st); break;
+        }
+    } else if (pl.nepi == 8) {
         switch (pl.tile_n) {
             case 64: e = launch_tc2<64, 8>(pl, grid, st); break;
             case 128: e = launch_tc2<128, 8>(pl, grid, st); break;
@@ -566,8 +571,11 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     const bool box = d.stride == 2;
     if ((d.out2 || d.q_on) && box) return 0;
     if (box ? (d.k != 3 || nepi != 4 || gw != 32) : (d.stride != 1)) return 0;
-    if (d.cout_pad % bn || (nepi != 4 && nepi != 8)) return 0;
+    if (d.cout_pad % bn || (nepi != 4 && nepi != 8 && nepi != 16)) return 0;
     if (!box && (d.cout % gw != 0 || (gw != 32 && (gw != 64 || nepi != 4)))) return 0;
+    // sixteen epilogue warps (four per TMEM lane quarter, one 32-column group each at N = 128, two at N = 256): four warps per
+    // scheduler instead of two hide the TMEM-load / MUFU / shared-store latencies of the epilogue, which is what bounds the 1x1 layers
+    if (nepi == 16 && (box || bn < 128 || d.q_on)) return 0;
     TcConvPlan P;
     TcParams& p = P.p;
     memset(&p, 0, sizeof(p));

@@ -855,12 +855,14 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
             if (allow_cta2)                                                      // CTA-pair kernel: {N tile, k-blocks per barrier, epilogue warps, group width}
                 for (int bn : {64, 128, 256})
                     for (int g : {1, 2, 3})
-                        for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}})
-                            cands.push_back({bn, 224, 0, g, 1, ep.first, 0, ep.second, 1});
+                        for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}, std::pair<int, int>{16, 32}})
+                            if (ep.first != 16 || (bn >= 128 && !(getenv("Y4_NEPI16") && getenv("Y4_NEPI16")[0] == '0')))
+                                cands.push_back({bn, 224, 0, g, 1, ep.first, 0, ep.second, 1});
             if (allow_cta2 && !(getenv("Y4_PATCH2") && getenv("Y4_PATCH2")[0] == '0'))   // CTA pair + A-patch reuse (3x3 stride 1): cuts the L2 -> smem traffic
                 for (int bn : {64, 128, 256})
-                    for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}})
+                    for (auto& ep : {std::pair<int, int>{8, 32}, std::pair<int, int>{4, 64}, std::pair<int, int>{4, 32}, std::pair<int, int>{16, 32}})
                         for (int g : {1, 2}) {
+                            if (ep.first == 16 && (bn < 128 || (getenv("Y4_NEPI16") && getenv("Y4_NEPI16")[0] == '0'))) continue;
                             // g = 2: deep B ring (tc_plan2: up to 12 weight stages beside three patches).  Measured: no gain on any layer
                             // (the six-stage ring already covers the L2 latency), so it stays out of the default list: Y4_DEEPB=1
                             if (g == 2 && !(getenv("Y4_DEEPB") && getenv("Y4_DEEPB")[0] == '1')) continue;
