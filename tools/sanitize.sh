@@ -16,6 +16,11 @@ run() {   # tool prec force
   local summ=$(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $log | tail -1 | sed 's/=========//')
   echo "| $1 | $2 | ${3:-default plans} | $([ $ok -ge 1 ] && echo ran || echo FAILED) | ${summ:-none printed} |" >> $out
 }
+if [ "$2" = "decode" ]; then      # tools/sanitize.sh <tag> decode: only the decode / NMS kernels (fast)
+  for tool in memcheck racecheck synccheck; do run $tool decode ""; done
+  cat $out
+  exit 0
+fi
 for tool in memcheck racecheck synccheck; do
   run $tool fp16 ""
   run $tool fp16 "128,224,0,1,1,4,0,32,0,0,0" 1

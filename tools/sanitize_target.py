@@ -1,5 +1,7 @@
 """Target of tools/sanitize.sh: one small forward (64x64, batch 2) + decode/NMS (fast path, long class segment, overflow path)
-through the C-ABI, for compute-sanitizer.  usage: python tools/sanitize_target.py fp16|fp16x3|fp32"""
+through the C-ABI, for compute-sanitizer.  usage: python tools/sanitize_target.py fp16|fp16x3|fp32|decode
+(decode: no forward, only the decode / NMS kernels on crafted heads at 128x128: every regime of nms_image_kernel -- class
+segments <= 64 (warp path), 65..704 (CTA-wide bit matrix), longer (sequential) -- the staged filter, and the overflow path)"""
 import os
 import sys
 
@@ -9,6 +11,32 @@ import numpy as np  # noqa: E402
 import y4b200  # noqa: E402
 import y4_oracle as O  # noqa: E402
 
+if sys.argv[1] == 'decode':
+    S, B = 128, 3
+    eng = y4b200.Engine(img_size=S, max_batch=B, precision=y4b200.PREC_FP16)
+    heads = O.synth_heads(seed=2, batch=B, img_size=S, n_clusters=60, num_classes=80)
+    r1 = eng.decode_nms(heads, with_indices=True)
+    ref = O.decode_nms(heads, S)
+    assert all(np.array_equal(r1[i], ref[i]) for i in (2, 3, 4)), 'decode/NMS differs from the oracle under the sanitizer'
+    res = [r1[3].tolist()]
+    for n_hot in (50, 150, 720):                                   # one class: warp path / bit matrix / sequential scan
+        one = [h.copy() for h in heads]
+        v = one[0].reshape(B, 16, 16, 3, 85)
+        idx = np.random.default_rng(n_hot).choice(16 * 16 * 3, n_hot, replace=False)
+        r, c, a = np.unravel_index(idx, (16, 16, 3))
+        v[:, r, c, a, 4] = 4.0
+        v[:, r, c, a, 5 + 3] = 4.0 + np.random.default_rng(1).uniform(0, 1, n_hot).astype(np.float32)
+        v[:, r, c, a, 2:4] += 1.0
+        got = eng.decode_nms(one, with_indices=True)
+        ref = O.decode_nms(one, S)
+        assert all(np.array_equal(got[i], ref[i]) for i in (2, 3, 4)), f'one-class segment of {n_hot} differs from the oracle'
+        res.append(got[3].tolist())
+    hot = [np.full_like(h, 3.0) for h in heads]                    # every (box, class) a candidate -> overflow path
+    res.append(eng.decode_nms(hot)[3].tolist())
+    res.append(eng.decode_nms(heads, 0.413, 0.999)[3].tolist())    # nothing passes
+    print('SANITIZE TARGET OK decode valid', res, flush=True)
+    eng.close()
+    sys.exit(0)
 prec = {'fp16': y4b200.PREC_FP16, 'fp16x3': y4b200.PREC_FP16X3, 'fp32': y4b200.PREC_FP32}[sys.argv[1]]
 S, B = 64, 2
 W = O.synth_weights(seed=1, calib_size=64)

@@ -352,15 +352,37 @@ __device__ __forceinline__ float mish_fast_nr(float acc, float b) {
     r = r * fmaf(-d, r, 2.f);
     return u * fmaf(r, -1.3862943611198906f, 0.6931471805599453f);
 }
+// Two mish values with ONE reciprocal: 1/d0 = rcp(d0 * d1) * d1, 1/d1 = rcp(d0 * d1) * d0 (d in [2, 2^59) thanks to the clamp of u,
+// so the product stays below 2^118).  Per pair: 3 MUFU (two ex2, one rcp) + 15 FMA-pipe / ALU instructions = 9 issue slots and
+// 1.5 MUFU per element, against 10.5 + 1.5 for the direct / Newton mix above: the 1x1 layers whose epilogue is issue-bound
+// (ncu: conv_tc2<256,16> issues 62 % of the cycles, 10 instructions per output element) gain the difference.
+__device__ __forceinline__ void mish_fast_pair(float acc0, float b0, float acc1, float b1, float& f0, float& f1) {
+    const float u0 = fmaf(acc0, 1.4426950408889634f, b0), u1 = fmaf(acc1, 1.4426950408889634f, b1);
+    const float a0 = ex2_approx(fminf(u0, 29.f)) + 1.f, a1 = ex2_approx(fminf(u1, 29.f)) + 1.f;
+    const float d0 = fmaf(a0, a0, 1.f), d1 = fmaf(a1, a1, 1.f);
+    const float r = rcp_approx(d0 * d1);
+    f0 = u0 * fmaf(r * d1, -1.3862943611198906f, 0.6931471805599453f);
+    f1 = u1 * fmaf(r * d0, -1.3862943611198906f, 0.6931471805599453f);
+}
 template <int ACT>
 __device__ __forceinline__ void act32_fast(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
-        f[j + 0] = act_fast<ACT>(__uint_as_float(v[j + 0]), b4.x);
-        f[j + 1] = ACT == 2 ? mish_fast_nr(__uint_as_float(v[j + 1]), b4.y) : act_fast<ACT>(__uint_as_float(v[j + 1]), b4.y);
-        f[j + 2] = act_fast<ACT>(__uint_as_float(v[j + 2]), b4.z);
-        f[j + 3] = ACT == 2 ? mish_fast_nr(__uint_as_float(v[j + 3]), b4.w) : act_fast<ACT>(__uint_as_float(v[j + 3]), b4.w);
+        if (ACT == 2) {
+            mish_fast_pair(__uint_as_float(v[j + 0]), b4.x, __uint_as_float(v[j + 1]), b4.y, f[j + 0], f[j + 1]);
+            mish_fast_pair(__uint_as_float(v[j + 2]), b4.z, __uint_as_float(v[j + 3]), b4.w, f[j + 2], f[j + 3]);
+        } else if (ACT == 3) {                              // the round-2b mix (direct / Newton), kept for A/B timing: Y4_MISH_OLD=1
+            f[j + 0] = act_fast<2>(__uint_as_float(v[j + 0]), b4.x);
+            f[j + 1] = mish_fast_nr(__uint_as_float(v[j + 1]), b4.y);
+            f[j + 2] = act_fast<2>(__uint_as_float(v[j + 2]), b4.z);
+            f[j + 3] = mish_fast_nr(__uint_as_float(v[j + 3]), b4.w);
+        } else {
+            f[j + 0] = act_fast<ACT>(__uint_as_float(v[j + 0]), b4.x);
+            f[j + 1] = act_fast<ACT>(__uint_as_float(v[j + 1]), b4.y);
+            f[j + 2] = act_fast<ACT>(__uint_as_float(v[j + 2]), b4.z);
+            f[j + 3] = act_fast<ACT>(__uint_as_float(v[j + 3]), b4.w);
+        }
     }
 }
 
@@ -462,6 +484,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams& p, const uint32_t
         else bias_act32<0>(v, sbias + col0, sscale + col0, f);
     } else {                                                // sbias holds b * log2(e) for mish layers (see act_fast)
         if (p.act == 2) act32_fast<2>(v, sbias + col0, f);
+        else if (p.act == 3) act32_fast<3>(v, sbias + col0, f);
         else if (p.act == 1) act32_fast<1>(v, sbias + col0, f);
         else act32_fast<0>(v, sbias + col0, f);
     }
@@ -548,6 +571,7 @@ __device__ __forceinline__ void epi_group(const TcParams& p, const uint32_t (&v)
     float f[32];
     const int act = act_sel < 0 ? p.act : act_sel;          // chain fusion: the second conv's activation
     if (act == 2) act32_fast<2>(v, sb, f);
+    else if (act == 3) act32_fast<3>(v, sb, f);
     else if (act == 1) act32_fast<1>(v, sb, f);
     else act32_fast<0>(v, sb, f);
     if (p.out_f32) {                                        // fp32 heads: 32 columns = one 128 B slab row (SWIZZLE_128B), no skip tensor
@@ -650,7 +674,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, SPLIT ? 1 : (LEAN ? 3 : 2)) co
     if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
     float* sscale = sbias + p.bias_n;
     // non-split mish layers keep b * log2(e) (act_fast)
-    const float bmul = (!SPLIT && p.act == 2) ? 1.4426950408889634f : 1.0f;
+    const float bmul = (!SPLIT && p.act >= 2) ? 1.4426950408889634f : 1.0f;
     // (weights, biases and scales are written once at load time, never by a preceding kernel: safe before pdl_wait)
     if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 32 * NEPI) { sbias[i] = p.bias[i] * bmul; sscale[i] = p.wscale ? p.wscale[i] : 1.0f; }
     tc_fence_before();
@@ -1242,6 +1266,7 @@ inline int tc_plan(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int bn
     p.act = d.act; p.out_f32 = d.out_f32; p.upsample = d.upsample;
     if (d.out_f32 && d.obj_out) { p.obj_out = d.obj_out; p.obj_c0 = d.obj_c0; p.obj_stride = d.obj_stride; p.obj_rows = d.obj_rows; }
     if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);
+    if (p.act == 2 && !d.split && getenv("Y4_MISH_OLD")) p.act = 3;                     // A/B timing of the mish epilogue (act32_fast<3>)
     if (getenv("Y4_DEBUG_NORES")) p.res = nullptr;                          // timing experiments only (wrong results)
     p.cout_store = d.out_f32 ? d.cout_pad : d.cout;
     p.ksize = d.k;

@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(64 + 32 * NEPI, 1) conv_tc2_kernel(const __gri
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) tmem_alloc_cg2(tmem_slot, TMEM_COLS);
-    const float bmul = p.act == 2 ? 1.4426950408889634f : 1.0f;          // mish layers keep b * log2(e) (act_fast)
+    const float bmul = p.act >= 2 ? 1.4426950408889634f : 1.0f;          // mish layers keep b * log2(e) (act_fast)
     if (warp >= 2) for (int i = threadIdx.x - 64; i < p.bias_n; i += 32 * NEPI) sbias[i] = p.bias[i] * bmul;
     if (warp >= 2 && p.q_on) for (int i = threadIdx.x - 64; i < p.q_n; i += 32 * NEPI) sbias2[i] = p.q_bias[i] * (p.q_act == 2 ? 1.4426950408889634f : 1.0f);
     tc_fence_before();
@@ -586,6 +586,7 @@ inline int tc_plan2(const TcConvDesc& d, TcConvPlan* pl, std::string* err, int b
     p.out_ld = d.out_ld; p.out_choff = d.out_choff; p.res_ld = d.res_ld; p.res_choff = d.res_choff;
     p.act = d.act;
     if (const char* env = getenv("Y4_DEBUG_ACT")) p.act = atoi(env);
+    if (p.act == 2 && getenv("Y4_MISH_OLD")) p.act = 3;                     // A/B timing of the mish epilogue (act32_fast<3>)
     if (getenv("Y4_DEBUG_NORES")) p.res = nullptr;                          // timing experiments only (wrong results)
     p.cout_store = d.cout;
     p.ksize = d.k;
