@@ -364,19 +364,49 @@ __device__ __forceinline__ void mish_fast_pair(float acc0, float b0, float acc1,
     f0 = u0 * fmaf(r * d1, -1.3862943611198906f, 0.6931471805599453f);
     f1 = u1 * fmaf(r * d0, -1.3862943611198906f, 0.6931471805599453f);
 }
+// Packed fp32 arithmetic (sm_100: fma / mul / add .f32x2 = FFMA2 / FMUL2 / FADD2, two lanes per issue slot).
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+    unsigned long long d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+// Four mish values: the same arithmetic as mish_fast_pair on packed lanes A = (e0, e1), B = (e2, e3); e0 shares its reciprocal with e2
+// and e1 with e3 (rcp(dA * dB) * dB, * dA), so no lane swap is needed.  13 packed FMA-pipe instructions + 4 FMNMX + 6 MUFU = 5.75
+// issue slots and 1.5 MUFU per element (pair version: 9 + 1.5): the MUFU pipe (4 lanes / clk / scheduler) is now the tighter bound.
+__device__ __forceinline__ void mish_fast_quad(const uint32_t (&v)[32], int j, const float4 b4, float (&f)[32]) {
+    const unsigned long long L2E = pk2(1.4426950408889634f, 1.4426950408889634f), ONE = pk2(1.f, 1.f);
+    const unsigned long long NEG = pk2(-1.3862943611198906f, -1.3862943611198906f), LN2 = pk2(0.6931471805599453f, 0.6931471805599453f);
+    const unsigned long long uA = fma2(pk2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1])), L2E, pk2(b4.x, b4.y));
+    const unsigned long long uB = fma2(pk2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), L2E, pk2(b4.z, b4.w));
+    float u0, u1, u2, u3;
+    upk2(uA, u0, u1); upk2(uB, u2, u3);
+    const unsigned long long tA = pk2(ex2_approx(fminf(u0, 29.f)), ex2_approx(fminf(u1, 29.f)));
+    const unsigned long long tB = pk2(ex2_approx(fminf(u2, 29.f)), ex2_approx(fminf(u3, 29.f)));
+    const unsigned long long aA = add2(tA, ONE), aB = add2(tB, ONE);
+    const unsigned long long dA = fma2(aA, aA, ONE), dB = fma2(aB, aB, ONE);        // each in [2, 2^59)
+    float p0, p1;
+    upk2(mul2(dA, dB), p0, p1);
+    const unsigned long long r = pk2(rcp_approx(p0), rcp_approx(p1));
+    const unsigned long long fA = mul2(uA, fma2(mul2(r, dB), NEG, LN2));
+    const unsigned long long fB = mul2(uB, fma2(mul2(r, dA), NEG, LN2));
+    upk2(fA, f[j + 0], f[j + 1]); upk2(fB, f[j + 2], f[j + 3]);
+}
 template <int ACT>
 __device__ __forceinline__ void act32_fast(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
 #pragma unroll
     for (int j = 0; j < 32; j += 4) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
         if (ACT == 2) {
+            mish_fast_quad(v, j, b4, f);
+        } else if (ACT == 3) {                              // the scalar pair version, kept for A/B timing: Y4_MISH_OLD=1
             mish_fast_pair(__uint_as_float(v[j + 0]), b4.x, __uint_as_float(v[j + 1]), b4.y, f[j + 0], f[j + 1]);
             mish_fast_pair(__uint_as_float(v[j + 2]), b4.z, __uint_as_float(v[j + 3]), b4.w, f[j + 2], f[j + 3]);
-        } else if (ACT == 3) {                              // the round-2b mix (direct / Newton), kept for A/B timing: Y4_MISH_OLD=1
-            f[j + 0] = act_fast<2>(__uint_as_float(v[j + 0]), b4.x);
-            f[j + 1] = mish_fast_nr(__uint_as_float(v[j + 1]), b4.y);
-            f[j + 2] = act_fast<2>(__uint_as_float(v[j + 2]), b4.z);
-            f[j + 3] = mish_fast_nr(__uint_as_float(v[j + 3]), b4.w);
         } else {
             f[j + 0] = act_fast<ACT>(__uint_as_float(v[j + 0]), b4.x);
             f[j + 1] = act_fast<ACT>(__uint_as_float(v[j + 1]), b4.y);
