@@ -397,21 +397,53 @@ __device__ __forceinline__ void mish_fast_quad(const uint32_t (&v)[32], int j, c
     const unsigned long long fB = mul2(uB, fma2(mul2(r, dA), NEG, LN2));
     upk2(fA, f[j + 0], f[j + 1]); upk2(fB, f[j + 2], f[j + 3]);
 }
+// Eight mish values with TWO reciprocals: lanes A..D = (e0,e1) .. (e6,e7); e0, e2, e4, e6 share rcp(dA dB dC dD) (low lanes), e1, e3,
+// e5, e7 the high lane's.  u is clamped at 14 instead of 29 (d < 2^29, so the product of four stays below 2^116); for u >= 14, i.e.
+// x >= 9.7, 2 / d < 2^-28 and g rounds to ln2 either way, so the result is the same x.  47 issue slots and 10 MUFU per 8 elements:
+// 5.9 issue slots + 1.25 MUFU per element (quad: 5.75 + 1.5): the MUFU pipe (one warp instruction per 8 cycles per scheduler) is
+// the tighter bound of the mish epilogue, 12 -> 10 pipe cycles per element.
+__device__ __forceinline__ void mish_fast_oct(const uint32_t (&v)[32], int j, const float4 b0, const float4 b1, float (&f)[32]) {
+    const unsigned long long L2E = pk2(1.4426950408889634f, 1.4426950408889634f), ONE = pk2(1.f, 1.f);
+    const unsigned long long NEG = pk2(-1.3862943611198906f, -1.3862943611198906f), LN2 = pk2(0.6931471805599453f, 0.6931471805599453f);
+    unsigned long long u[4], d[4];
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        u[k] = fma2(pk2(__uint_as_float(v[j + 2 * k]), __uint_as_float(v[j + 2 * k + 1])), L2E, pk2(bb[2 * k], bb[2 * k + 1]));
+        float lo, hi;
+        upk2(u[k], lo, hi);
+        const unsigned long long a = add2(pk2(ex2_approx(fminf(lo, 14.f)), ex2_approx(fminf(hi, 14.f))), ONE);
+        d[k] = fma2(a, a, ONE);                             // in [2, 2^29)
+    }
+    const unsigned long long pAB = mul2(d[0], d[1]), pCD = mul2(d[2], d[3]);
+    float p0, p1;
+    upk2(mul2(pAB, pCD), p0, p1);
+    const unsigned long long r = pk2(rcp_approx(p0), rcp_approx(p1));
+    const unsigned long long rAB = mul2(r, pCD), rCD = mul2(r, pAB);      // 1 / (dA dB), 1 / (dC dD)
+    const unsigned long long ri[4] = {mul2(rAB, d[1]), mul2(rAB, d[0]), mul2(rCD, d[3]), mul2(rCD, d[2])};
+#pragma unroll
+    for (int k = 0; k < 4; k++) upk2(mul2(u[k], fma2(ri[k], NEG, LN2)), f[j + 2 * k], f[j + 2 * k + 1]);
+}
 template <int ACT>
 __device__ __forceinline__ void act32_fast(const uint32_t (&v)[32], const float* __restrict__ bias, float (&f)[32]) {
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
+    for (int j = 0; j < 32; j += 8) {
         const float4 b4 = *reinterpret_cast<const float4*>(bias + j);
+        const float4 b5 = *reinterpret_cast<const float4*>(bias + j + 4);
         if (ACT == 2) {
+            mish_fast_oct(v, j, b4, b5, f);
+        } else if (ACT == 3) {                              // the four-element version, kept for A/B timing: Y4_MISH_OLD=1
             mish_fast_quad(v, j, b4, f);
-        } else if (ACT == 3) {                              // the scalar pair version, kept for A/B timing: Y4_MISH_OLD=1
-            mish_fast_pair(__uint_as_float(v[j + 0]), b4.x, __uint_as_float(v[j + 1]), b4.y, f[j + 0], f[j + 1]);
-            mish_fast_pair(__uint_as_float(v[j + 2]), b4.z, __uint_as_float(v[j + 3]), b4.w, f[j + 2], f[j + 3]);
+            mish_fast_quad(v, j + 4, b5, f);
         } else {
             f[j + 0] = act_fast<ACT>(__uint_as_float(v[j + 0]), b4.x);
             f[j + 1] = act_fast<ACT>(__uint_as_float(v[j + 1]), b4.y);
             f[j + 2] = act_fast<ACT>(__uint_as_float(v[j + 2]), b4.z);
             f[j + 3] = act_fast<ACT>(__uint_as_float(v[j + 3]), b4.w);
+            f[j + 4] = act_fast<ACT>(__uint_as_float(v[j + 4]), b5.x);
+            f[j + 5] = act_fast<ACT>(__uint_as_float(v[j + 5]), b5.y);
+            f[j + 6] = act_fast<ACT>(__uint_as_float(v[j + 6]), b5.z);
+            f[j + 7] = act_fast<ACT>(__uint_as_float(v[j + 7]), b5.w);
         }
     }
 }
