@@ -436,14 +436,22 @@ __device__ __forceinline__ void act32_fast(const uint32_t (&v)[32], const float*
             mish_fast_quad(v, j, b4, f);
             mish_fast_quad(v, j + 4, b5, f);
         } else {
-            f[j + 0] = act_fast<ACT>(__uint_as_float(v[j + 0]), b4.x);
-            f[j + 1] = act_fast<ACT>(__uint_as_float(v[j + 1]), b4.y);
-            f[j + 2] = act_fast<ACT>(__uint_as_float(v[j + 2]), b4.z);
-            f[j + 3] = act_fast<ACT>(__uint_as_float(v[j + 3]), b4.w);
-            f[j + 4] = act_fast<ACT>(__uint_as_float(v[j + 4]), b5.x);
-            f[j + 5] = act_fast<ACT>(__uint_as_float(v[j + 5]), b5.y);
-            f[j + 6] = act_fast<ACT>(__uint_as_float(v[j + 6]), b5.z);
-            f[j + 7] = act_fast<ACT>(__uint_as_float(v[j + 7]), b5.w);
+            // leaky / linear on packed lanes: x = acc + b (FADD2), 0.1 x (FMUL2), max per lane -- the same round-to-nearest operations
+            // as act_fast<ACT>, so the bits are those of the scalar form
+            const float bb[8] = {b4.x, b4.y, b4.z, b4.w, b5.x, b5.y, b5.z, b5.w};
+            const unsigned long long TENTH = pk2(0.1f, 0.1f);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const unsigned long long x = add2(pk2(__uint_as_float(v[j + 2 * k]), __uint_as_float(v[j + 2 * k + 1])), pk2(bb[2 * k], bb[2 * k + 1]));
+                float x0, x1;
+                upk2(x, x0, x1);
+                if (ACT == 1) {
+                    float y0, y1;
+                    upk2(mul2(x, TENTH), y0, y1);
+                    x0 = fmaxf(x0, y0); x1 = fmaxf(x1, y1);
+                }
+                f[j + 2 * k] = x0; f[j + 2 * k + 1] = x1;
+            }
         }
     }
 }

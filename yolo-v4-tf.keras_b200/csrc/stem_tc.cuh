@@ -211,10 +211,12 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_tc_kernel(const __grid_c
                 for (int c4 = 0; c4 < 4; c4++) {
                     __half2 h[4];
 #pragma unroll
-                    for (int t4 = 0; t4 < 4; t4++) {
-                        float u0 = __uint_as_float(acc[8 * c4 + 2 * t4]) + sbias0[8 * c4 + 2 * t4];
-                        float u1 = __uint_as_float(acc[8 * c4 + 2 * t4 + 1]) + sbias0[8 * c4 + 2 * t4 + 1];
-                        h[t4] = __floats2half2_rn(fmaxf(u0, 0.1f * u0), fmaxf(u1, 0.1f * u1));     // leaky (custom_layers.py:101)
+                    for (int t4 = 0; t4 < 4; t4++) {                                               // packed fp32 (FADD2 / FMUL2): same bits as the scalar form
+                        const unsigned long long u = add2(pk2(__uint_as_float(acc[8 * c4 + 2 * t4]), __uint_as_float(acc[8 * c4 + 2 * t4 + 1])),
+                                                          *reinterpret_cast<const unsigned long long*>(sbias0 + 8 * c4 + 2 * t4));
+                        float u0, u1, y0, y1;
+                        upk2(u, u0, u1); upk2(mul2(u, pk2(0.1f, 0.1f)), y0, y1);
+                        h[t4] = __floats2half2_rn(fmaxf(u0, y0), fmaxf(u1, y1));                   // leaky (custom_layers.py:101)
                     }
                     uint4 o;
                     o.x = *reinterpret_cast<uint32_t*>(&h[0]); o.y = *reinterpret_cast<uint32_t*>(&h[1]);
@@ -262,9 +264,11 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_tc_kernel(const __grid_c
                 __half2 h[4];
 #pragma unroll
                 for (int t4 = 0; t4 < 4; t4++) {
-                    const float u0 = __uint_as_float(acc[8 * c4 + 2 * t4]) + sbias1[32 * set + 8 * c4 + 2 * t4];
-                    const float u1 = __uint_as_float(acc[8 * c4 + 2 * t4 + 1]) + sbias1[32 * set + 8 * c4 + 2 * t4 + 1];
-                    h[t4] = __floats2half2_rn(fmaxf(u0, 0.1f * u0), fmaxf(u1, 0.1f * u1));         // leaky (custom_layers.py:102)
+                    const unsigned long long u = add2(pk2(__uint_as_float(acc[8 * c4 + 2 * t4]), __uint_as_float(acc[8 * c4 + 2 * t4 + 1])),
+                                                      *reinterpret_cast<const unsigned long long*>(sbias1 + 32 * set + 8 * c4 + 2 * t4));
+                    float u0, u1, y0, y1;
+                    upk2(u, u0, u1); upk2(mul2(u, pk2(0.1f, 0.1f)), y0, y1);
+                    h[t4] = __floats2half2_rn(fmaxf(u0, y0), fmaxf(u1, y1));                       // leaky (custom_layers.py:102)
                 }
                 uint4 o;
                 o.x = *reinterpret_cast<uint32_t*>(&h[0]); o.y = *reinterpret_cast<uint32_t*>(&h[1]);
