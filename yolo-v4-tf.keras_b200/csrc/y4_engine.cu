@@ -108,7 +108,7 @@ struct y4_engine {
     unsigned long long* d_win_keys = nullptr;          // NMS workspace of the overflow path (decode_nms.cuh)
     int* d_nwin = nullptr;
     unsigned long long* d_part_keys = nullptr;         // nms_image_kernel: per-part survivor lists, [B][kMaxParts][kMaxBoxesCap]
-    int* d_ticket = nullptr;                           // [B], zero between launches
+    int* d_ticket = nullptr;                           // [B], = d_cand_count + B: cleared with it at the start of every decode
     int* d_cand_count = nullptr;
     float4* d_boxes = nullptr;
     float* d_out_boxes = nullptr; float* d_out_scores = nullptr; float* d_out_classes = nullptr;
@@ -518,7 +518,8 @@ int run_decode_nms(y4_engine* e, int batch, float iou_thr, float score_thr, cons
         else { const double lt = log(t / (1.0 - t)); d.logit_lo = (float)(lt - 1e-3 - 1e-3 * fabs(lt)); }
     }
     d.cand_keys = e->d_cand_keys; d.cand_count = e->d_cand_count; d.boxes = e->d_boxes;
-    CUDA_TRY(e, cudaMemsetAsync(e->d_cand_count, 0, sizeof(int) * batch, e->stream));
+    // candidate counts AND the NMS parts' tickets (contiguous): a launch that died half way must not leave a ticket behind
+    CUDA_TRY(e, cudaMemsetAsync(e->d_cand_count, 0, sizeof(int) * 2 * e->cfg.max_batch, e->stream));
     decode_filter_kernel<<<dim3((unsigned)((e->N + kFilterThreads - 1) / kFilterThreads), (unsigned)batch), kFilterThreads, 0, e->stream>>>(d);
     NmsParams n{};
     n.cand_keys = e->d_cand_keys; n.cand_count = e->d_cand_count; n.boxes = e->d_boxes;
@@ -733,12 +734,11 @@ int y4_create(y4_engine** out, const y4_config* cfg) {
         CREATE_TRY(cudaMemset(e->d_obj[i], 0, sizeof(float) * 3 * e->obj_rows[i]));
     }
     CREATE_TRY(cudaMalloc(&e->d_cand_keys, sizeof(unsigned long long) * kCandCap * B));
-    CREATE_TRY(cudaMalloc(&e->d_cand_count, sizeof(int) * B));
+    CREATE_TRY(cudaMalloc(&e->d_cand_count, sizeof(int) * 2 * B));
+    e->d_ticket = e->d_cand_count + B;
     CREATE_TRY(cudaMalloc(&e->d_win_keys, sizeof(unsigned long long) * (size_t)cfg->num_classes * mb * B));
     CREATE_TRY(cudaMalloc(&e->d_nwin, sizeof(int) * 256 * B));
     CREATE_TRY(cudaMalloc(&e->d_part_keys, sizeof(unsigned long long) * kMaxParts * kMaxBoxesCap * B));
-    CREATE_TRY(cudaMalloc(&e->d_ticket, sizeof(int) * B));
-    CREATE_TRY(cudaMemset(e->d_ticket, 0, sizeof(int) * B));
     CREATE_TRY(cudaMalloc(&e->d_boxes, sizeof(float4) * e->N * B));
     CREATE_TRY(cudaMemset(e->d_boxes, 0, sizeof(float4) * e->N * B));
     CREATE_TRY(cudaMalloc(&e->d_out_boxes, sizeof(float) * 4 * mb * B));
@@ -1005,7 +1005,7 @@ void y4_destroy(y4_engine* e) {
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 3; i++) { cudaFree(e->d_user_heads[i]); cudaFree(e->d_obj[i]); }
     cudaFree(e->d_cand_keys); cudaFree(e->d_cand_count); cudaFree(e->d_boxes);
-    cudaFree(e->d_win_keys); cudaFree(e->d_nwin); cudaFree(e->d_part_keys); cudaFree(e->d_ticket);
+    cudaFree(e->d_win_keys); cudaFree(e->d_nwin); cudaFree(e->d_part_keys);
     cudaFree(e->d_out_boxes); cudaFree(e->d_out_scores); cudaFree(e->d_out_classes);
     cudaFree(e->d_out_valid); cudaFree(e->d_out_idx);
     cudaFree(e->d_flush); cudaFree(e->d_gather);
