@@ -24,17 +24,17 @@ for line in sass.splitlines():
     if m and cur:
         kernels[cur][m.group(1)] += 1
 names = subprocess.run(['c++filt'], input='\n'.join(kernels), capture_output=True, text=True).stdout.splitlines()
-KEY = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'LDGSTS', 'SYNCS', 'HMMA', 'FFMA', 'MUFU', 'LDG', 'STG', 'LDS', 'STS', 'BAR']
+KEY = ['UTCHMMA', 'UTCBAR', 'LDTM', 'STTM', 'UTMALDG', 'UTMASTG', 'UTMAPF', 'LDGSTS', 'SYNCS', 'HMMA', 'FFMA', 'FFMA2', 'FMUL2', 'FADD2', 'MUFU', 'LDG', 'STG', 'LDS', 'STS', 'BAR']
 out = [f'# SASS opcode histogram per kernel of liby4.so ({tag}; cuobjdump -sass, sm_100a)', '',
        'Counts of static instructions.  `UTCHMMA` = tcgen05.mma (`.2CTA` = cta_group::2), `LDTM` = tcgen05.ld, `UTMALDG` / `UTMASTG` = TMA',
-       'load / store, `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops, `LDGSTS` = cp.async.  No `HMMA` (legacy mma.sync) anywhere.', '',
+       'load / store, `UTCBAR` = tcgen05.commit, `SYNCS` = mbarrier ops, `LDGSTS` = cp.async, `FFMA2` / `FMUL2` / `FADD2` = packed fp32 (.f32x2) in the epilogues.  No `HMMA` (legacy mma.sync) anywhere.', '',
        '| kernel | total | ' + ' | '.join(KEY) + ' |', '|---|---|' + '---|' * len(KEY)]
 tot = collections.Counter()
 for (mangled, c), nice in zip(kernels.items(), names):
     nice = re.sub(r'\(.*\)$', '', nice).replace('void ', '').replace('y4::', '')
     row = []
     for k in KEY:
-        n = sum(v for op, v in c.items() if op == k or op.startswith(k + '.'))
+        n = sum(v for op, v in c.items() if op == k or op.startswith(k + '.'))      # exact mnemonic: FFMA does not count FFMA2
         if k == 'UTCHMMA':
             n2 = sum(v for op, v in c.items() if op.startswith('UTCHMMA') and '2CTA' in op)
             row.append(f'{n} ({n2} .2CTA)' if n2 else str(n))
