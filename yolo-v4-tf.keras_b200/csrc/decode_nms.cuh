@@ -11,7 +11,7 @@ namespace y4 {
 constexpr int kCandCap = 8192;     // Y4_MAX_CANDIDATES: candidate-list capacity per image of the FAST path; images with more
                                    // candidates are handled exactly by nms_overflow_kernel (no limit, as in TF)
 constexpr int kSelCap = 8192;      // >= num_classes * max_boxes
-constexpr int kMaxBoxesCap = 128;  // max_boxes upper bound (per-warp selected list in smem)
+constexpr int kMaxBoxesCap = 128;  // max_boxes upper bound (selected lists in smem, per-part survivor lists in global memory)
 
 struct DecodeParams {
     const float* head[3];
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(kImgThreads, 1) nms_image_kernel(NmsParams p) 
 // boxes whose class score passes the threshold (same arithmetic as decode_filter_kernel, so the same candidate set); then at
 // most max_boxes rounds, each ONE sweep over the still-alive boxes: suppress against the box selected in the previous round
 // (iou > thr strict) and find the best remaining (score desc, box asc) -- identical to TF's sorted greedy scan, without ever
-// materialising or sorting the candidate list.  Launched after nms_class_kernel on every step; returns at once for images
+// materialising or sorting the candidate list.  Launched after nms_image_kernel on every step; returns at once for images
 // that fitted the fast path.
 constexpr int kOverflowThreads = 256;
 __global__ void __launch_bounds__(kOverflowThreads) nms_overflow_kernel(DecodeParams d, NmsParams p) {
