@@ -213,3 +213,22 @@ def test_facade_host_logic_with_stub_engine(tmp_path, monkeypatch):
     assert len(lines) == 2
     cls, score, x1, y1, x2, y2 = lines[0].split(' ')
     assert cls == 'person' and float(score) == pytest.approx(0.9) and float(x2) == pytest.approx(0.5 * 50) and float(y2) == pytest.approx(0.75 * 103)
+
+
+def test_library_sass_is_tcgen05_tma_and_packed_fp32():
+    """The shipped liby4.so is sm_100a code whose conv kernels issue tcgen05.mma (UTCHMMA, incl. the cta_group::2 form), read
+    TMEM (LDTM), move tiles by TMA (UTMALDG / UTMASTG) and run the mish epilogue on packed fp32 (FFMA2); no legacy mma.sync
+    (HMMA) anywhere.  Static check with cuobjdump (skipped where the CUDA toolkit is absent)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    import y4b200
+    sass = subprocess.run([cuobjdump, '-sass', y4b200.lib_path()], capture_output=True, text=True, check=True).stdout
+    assert 'sm_100a' in sass or 'SM100a' in sass or 'sm_100' in sass
+    count = {k: len(re.findall(r'\b' + k + r'\b', sass)) for k in ('UTCHMMA', 'LDTM', 'UTMALDG', 'UTMASTG', 'FFMA2', 'HMMA')}
+    count['UTCHMMA.2CTA'] = sass.count('UTCHMMA.2CTA')
+    assert count['UTCHMMA'] > 500 and count['UTCHMMA.2CTA'] > 100 and count['LDTM'] > 20, count
+    assert count['UTMALDG'] > 100 and count['UTMASTG'] > 10 and count['FFMA2'] > 1000, count
+    assert count['HMMA'] == 0, count
